@@ -1,0 +1,165 @@
+/*
+ * jues_b200.h -- C ABI of libjues_b200.so, the B200 (sm_100a) implementation of the JuES.jl
+ * hot path: 4-index AO->MO ERI transformation, RMP2 energy, RCCD / RCCSD amplitude iterations.
+ *
+ * The reference (mdav2/JuES.jl) has no FFI layer: its boundary is a set of Julia method
+ * signatures.  Each entry point below sits *under* one of them and is reached with `ccall` from
+ * a thin Julia shim (jues.jl_b200/julia/JuESB200.jl) or with ctypes (jues.jl_b200/__init__.py).
+ * Citations are file:line in the reference tree.
+ *
+ * Conventions
+ *   - every array is column-major IEEE FP64 exactly as Julia holds an Array{Float64,N}
+ *     (element [i1,i2,i3,i4] of a (d1,d2,d3,d4) array at i1 + d1*(i2 + d2*(i3 + d3*i4)), 0-based);
+ *     dims are int64_t (Julia Int).
+ *   - pointers named *_host / plain `const double*` arguments are HOST pointers owned by the
+ *     caller; the library never keeps them after the call returns.
+ *   - calls are blocking and one-at-a-time per context (the reference entry points are
+ *     single-task and blocking).
+ *   - return 0 on success, a negative JUES_B200_E* code otherwise; the message is available
+ *     from jues_b200_last_error().  No exception, exit() or signal crosses the ABI.
+ *   - there is NO CPU fallback: without a CUDA device jues_b200_init fails with JUES_B200_ECUDA.
+ */
+#ifndef JUES_B200_H
+#define JUES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JUES_B200_OK       0
+#define JUES_B200_EINVAL  -1   /* bad shape / null pointer / unknown option            */
+#define JUES_B200_ENOMEM  -2   /* device (or pinned host) capacity exceeded            */
+#define JUES_B200_ECUDA   -3   /* CUDA runtime / driver error, or no device            */
+#define JUES_B200_ENCCL   -4   /* NCCL error or NCCL library not loadable              */
+#define JUES_B200_ESTATE  -5   /* call not valid in the current state of the handle    */
+
+typedef struct jues_ctx jues_ctx;   /* opaque: device, stream, workspaces, communicator    */
+typedef struct jues_t4  jues_t4;    /* opaque: device-resident rank-4 tensor (see below)    */
+
+/* ---- context ------------------------------------------------------------------------- */
+/* Create a context on CUDA device `device` (one context = one GPU = one process rank).     */
+int  jues_b200_init(jues_ctx** ctx, int device);
+void jues_b200_finalize(jues_ctx* ctx);
+/* Message of the last failing call on this context ("" if none). ctx==NULL: global message
+ * of a failed jues_b200_init.                                                              */
+const char* jues_b200_last_error(jues_ctx* ctx);
+/* Library / build identification: "jues_b200 <version> sm_100a".                           */
+const char* jues_b200_version(void);
+
+/* Multi-GPU (one process per GPU): attach rank/size and an NCCL unique id (128 bytes, made by
+ * rank 0 with jues_b200_nccl_unique_id and broadcast by the host program, e.g. through
+ * torch.distributed / MPI / a file).  Collectives used on the path: all-gather of the new T2
+ * slab and all-reduce of energy partials.  The reference's only
+ * multi-process design is ParCCD.jl:23-86,241-295 (Julia Distributed, slabs over virtual b).  */
+int jues_b200_nccl_unique_id(unsigned char id_out[128]);
+int jues_b200_init_dist(jues_ctx* ctx, int rank, int nranks, const unsigned char id[128]);
+
+/* ---- BLAS.gemm! replacement ----------------------------------------------------------- */
+/* C = alpha*op(A)*op(B) + beta*C, column-major, host pointers.  Replaces the explicit
+ * `BLAS.gemm!` calls of src/CoupledCluster/mRCCD.jl:268-274,289-297,314-389,408-485 and is the
+ * kernel every contraction of the path is built from (FP64 DMMA tiles fed by TMA).
+ * transA/transB: 'N' or 'T'.                                                               */
+int jues_b200_dgemm(jues_ctx* ctx, char transA, char transB, int64_t M, int64_t N, int64_t K,
+                    double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                    double beta, double* C, int64_t ldc);
+
+/* ---- Transformation.tei_transform (src/Backend/Transformation.jl:15-26, 39-93) ---------- */
+/* out[i,a,j,b] = sum_{mu nu lam sig} C1[mu,i] C2[nu,a] C3[lam,j] C4[sig,b] gao[mu,nu,lam,sig]
+ * gao: (nao,nao,nao,nao); Ck: (nao,dk); out: (d1,d2,d3,d4) in chemists' order, or, when
+ * phys_order != 0, permuted [1,3,2,4] -> (d1,d3,d2,d4) as every caller of the reference does
+ * (RCCD.jl:91-95, RCCSD.jl:118-132; IntegralTransformation.jl:96-98).                       */
+int jues_b200_tei_transform(jues_ctx* ctx, const double* gao, int64_t nao,
+                            const double* C1, int64_t d1, const double* C2, int64_t d2,
+                            const double* C3, int64_t d3, const double* C4, int64_t d4,
+                            int phys_order, double* out);
+
+/* ---- MollerPlesset.do_rmp2 (src/MollerPlesset/RMP2.jl:11-45) ---------------------------- */
+/* E = sum_{ijab} v_ijab (2 v_ijab - v_ijba) / (eps_i + eps_j - eps_a - eps_b), v = <ij|ab>.
+ * eps: (nocc+nvir) orbital energies, occupied first (Wfn.epsa, Wavefunction.jl:85).         */
+int jues_b200_rmp2(jues_ctx* ctx, const double* gao, int64_t nao,
+                   const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                   const double* eps, double* e_mp2);
+
+/* ---- CoupledCluster.RCCD.do_rccd (src/CoupledCluster/RCCD.jl:33-83) --------------------- */
+/* maxit Jacobi sweeps with no convergence test (reference: maxit = 40, RCCD.jl:34,55).
+ * guess_mode 0 = reference guess T2 = (ij|ab)/D (RCCD.jl:45,145-160); 1 = MP2 guess.
+ * e_hist (nullable): [maxit+1] energies, e_hist[0] = energy of the guess, e_hist[k] after
+ * sweep k.  T2_out (nullable): (nocc,nocc,nvir,nvir) final amplitudes (return_T2, RCCD.jl:36,78).
+ * Returns the correlation energy of the last sweep in *e_ccd (RCCD.jl:81).                  */
+int jues_b200_rccd(jues_ctx* ctx, const double* gao, int64_t nao,
+                   const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                   const double* eps, int maxit, int guess_mode,
+                   double* e_ccd, double* e_hist, double* T2_out);
+
+/* ---- CoupledCluster.RCCSD.do_rccsd (src/CoupledCluster/RCCSD.jl:33-116) ----------------- */
+/* T1 = 0, T2 = <ij|ab>/D guess (RCCSD.jl:70,80); maxit sweeps (reference: 40, RCCSD.jl:36,88);
+ * both updates use the old amplitudes (RCCSD.jl:160-169).  e_hist as above (the reference
+ * prints it every sweep, RCCSD.jl:104).  T1_out (nocc,nvir), T2_out (nocc,nocc,nvir,nvir)
+ * nullable (return_T, RCCSD.jl:111-115).                                                    */
+int jues_b200_rccsd(jues_ctx* ctx, const double* gao, int64_t nao,
+                    const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                    const double* eps, int maxit,
+                    double* e_ccsd, double* e_hist, double* T1_out, double* T2_out);
+
+/* Per-sweep amplitude capture for parity tests: called (on the host, from inside
+ * jues_b200_rccd / _rccsd) after the guess (it = 0) and after every sweep with host copies of
+ * the amplitudes in the caller-visible (unpadded) layout.  T1 is NULL for RCCD.  Set to NULL to
+ * disable (default).                                                                        */
+typedef void (*jues_b200_amp_cb)(void* user, int it, double energy,
+                                 const double* T1, const double* T2);
+int jues_b200_set_amplitude_callback(jues_ctx* ctx, jues_b200_amp_cb cb, void* user);
+
+/* ---- device-resident rank-4 tensor: the DiskFourTensor replacement ---------------------- */
+/* src/DiskTensors/DiskFourTensors.jl:5-95 keeps a rank-4 Float64 tensor in an HDF5 file with
+ * slice getindex / setindex!, eltype and blockfill!.  Here the tensor lives in HBM (on the
+ * context's GPU) behind the same surface; ranges are 0-based half-open [lo,hi) per index.    */
+int jues_b200_t4_create(jues_ctx* ctx, int64_t d1, int64_t d2, int64_t d3, int64_t d4, jues_t4** out);
+int jues_b200_t4_destroy(jues_t4* t);
+int jues_b200_t4_dims(const jues_t4* t, int64_t dims_out[4]);
+int jues_b200_t4_fill(jues_t4* t, double value);                            /* blockfill! :88-95 */
+int jues_b200_t4_set_slice(jues_t4* t, const int64_t lo[4], const int64_t hi[4], const double* host); /* setindex! :57-80 */
+int jues_b200_t4_get_slice(const jues_t4* t, const int64_t lo[4], const int64_t hi[4], double* host); /* getindex :43-53 */
+/* Fill with the counter-based synthetic 8-fold-symmetric ERIs of SURVEY.md section 8d
+ * (bit-identical to jues.jl_b200.synth.counter_eri on the host).                             */
+int jues_b200_t4_synth_eri(jues_t4* t, uint64_t seed, double scale);
+
+/* Entry points taking a device-resident gao (Wfn.ao_eri::DiskFourTensor dispatch,
+ * Wavefunction.jl:87; Transformation.jl:94-192).  Inputs are already in HBM when they start. */
+int jues_b200_tei_transform_t4(jues_ctx* ctx, const jues_t4* gao,
+                               const double* C1, int64_t d1, const double* C2, int64_t d2,
+                               const double* C3, int64_t d3, const double* C4, int64_t d4,
+                               int phys_order, jues_t4** out);
+int jues_b200_rmp2_t4(jues_ctx* ctx, const jues_t4* gao,
+                      const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                      const double* eps, double* e_mp2);
+int jues_b200_rccd_t4(jues_ctx* ctx, const jues_t4* gao,
+                      const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                      const double* eps, int maxit, int guess_mode,
+                      double* e_ccd, double* e_hist, double* T2_out);
+int jues_b200_rccsd_t4(jues_ctx* ctx, const jues_t4* gao,
+                       const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                       const double* eps, int maxit,
+                       double* e_ccsd, double* e_hist, double* T1_out, double* T2_out);
+
+/* ---- instrumentation (bench.py) ---------------------------------------------------------- */
+/* Statistics of the last entry-point call on this context: CUDA-event milliseconds per phase
+ * on the library's stream, FP64 flops issued by the GEMM kernels, kernel launch counts.
+ * Keys: see DESIGN.md ("instrumentation").  Returns the number of phases written.            */
+typedef struct {
+    char   name[48];
+    double ms;
+} jues_b200_phase;
+int jues_b200_get_phases(jues_ctx* ctx, jues_b200_phase* out, int cap);
+int jues_b200_get_counters(jues_ctx* ctx, double* gemm_flops, int64_t* gemm_launches,
+                           int64_t* aux_launches, int64_t* bytes_peak);
+/* Time `reps` back-to-back launches of the DGEMM kernel on device-resident random operands
+ * (no host traffic); returns average ms per launch.  Used for the roofline line.            */
+int jues_b200_dgemm_bench(jues_ctx* ctx, char transA, char transB, int64_t M, int64_t N, int64_t K,
+                          int reps, double* ms_avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JUES_B200_H */

@@ -1,0 +1,135 @@
+// Host launcher of the sm_100a TMA + DMMA FP64 GEMM: builds the TMA tensor maps, picks a tile
+// configuration, launches on the context's stream.
+#include "dgemm.h"
+#include "dgemm_sm100.cuh"
+
+namespace jues {
+
+using namespace gemm;
+
+namespace {
+
+struct Cfg {
+    int BM, BN, WM, WN, STAGES;
+    const char* name;
+    double cost;  // relative cost per tile-flop (smaller tiles re-read operands more often)
+};
+// all configurations use 8 consumer warps + 1 producer warp
+static const Cfg kCfgs[] = {
+    {128, 128, 64, 32, 4, "128x128x16_w64x32_s4", 1.00},
+    {64, 128, 32, 32, 6, "64x128x16_w32x32_s6", 1.12},
+    {128, 64, 64, 16, 6, "128x64x16_w64x16_s6", 1.12},
+    {64, 64, 32, 16, 8, "64x64x16_w32x16_s8", 1.30},
+};
+constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
+
+typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const Params);
+
+template <bool A_KC, bool B_KC>
+KernelFn kernel_for(int cfg, int* smem) {
+    switch (cfg) {
+        case 0: *smem = SmemLayout<128, 128, 4>::TOTAL; return dgemm_tma_dmma<A_KC, B_KC, 128, 128, 64, 32, 4>;
+        case 1: *smem = SmemLayout<64, 128, 6>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 64, 128, 32, 32, 6>;
+        case 2: *smem = SmemLayout<128, 64, 6>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 128, 64, 64, 16, 6>;
+        default: *smem = SmemLayout<64, 64, 8>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 64, 64, 32, 16, 8>;
+    }
+}
+
+KernelFn pick_kernel(bool a_kc, bool b_kc, int cfg, int* smem) {
+    if (a_kc) return b_kc ? kernel_for<true, true>(cfg, smem) : kernel_for<true, false>(cfg, smem);
+    return b_kc ? kernel_for<false, true>(cfg, smem) : kernel_for<false, false>(cfg, smem);
+}
+
+void make_map(jues_ctx* ctx, CUtensorMap* map, const double* base, int64_t d0, int64_t d1,
+              int64_t ld, int64_t batch, int64_t bstride, int box0, int box1) {
+    JUES_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "GEMM operand must be 16-byte aligned");
+    JUES_REQUIRE((ld & 1) == 0 && ld >= d0, "GEMM operand leading dimension must be even and >= rows");
+    JUES_REQUIRE(batch == 1 || (bstride & 1) == 0, "GEMM batch stride must be even");
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)batch};
+    cuuint64_t bs = batch == 1 ? (cuuint64_t)ld * (cuuint64_t)d1 * 8ull : (cuuint64_t)bstride * 8ull;
+    if (bs == 0) bs = 16;
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8ull, bs};
+    cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims,
+                             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[256];
+        snprintf(buf, sizeof buf,
+                 "cuTensorMapEncodeTiled failed (%d) dims=(%lld,%lld,%lld) ld=%lld bstride=%lld box=(%d,%d)",
+                 (int)r, (long long)d0, (long long)d1, (long long)batch, (long long)ld,
+                 (long long)bstride, box0, box1);
+        throw Error(JUES_B200_ECUDA, buf);
+    }
+}
+
+int choose_cfg(jues_ctx* ctx, int64_t M, int64_t N, int64_t batch) {
+    int best = 0;
+    double best_t = 1e300;
+    const double sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    for (int c = 0; c < kNumCfgs; ++c) {
+        const double tiles = (double)((M + kCfgs[c].BM - 1) / kCfgs[c].BM) *
+                             (double)((N + kCfgs[c].BN - 1) / kCfgs[c].BN) * (double)batch;
+        const double waves = ceil(tiles / sms);
+        const double t = waves * kCfgs[c].BM * kCfgs[c].BN * kCfgs[c].cost;
+        if (t < best_t * 0.999) {
+            best_t = t;
+            best = c;
+        }
+    }
+    return best;
+}
+
+}  // namespace
+
+int dgemm_num_configs() { return kNumCfgs; }
+const char* dgemm_config_name(int cfg) { return (cfg >= 0 && cfg < kNumCfgs) ? kCfgs[cfg].name : "?"; }
+
+void dgemm(jues_ctx* ctx, const GemmCall& g) {
+    if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return;
+    JUES_REQUIRE(g.K > 0, "GEMM with K == 0");
+    JUES_REQUIRE(g.A && g.B && g.C, "GEMM null operand");
+    JUES_REQUIRE(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "GEMM dimension too large");
+    JUES_REQUIRE(g.ldc >= g.M, "GEMM ldc < M");
+    const bool a_kc = g.transA;   // A stored K x M
+    const bool b_kc = !g.transB;  // B stored K x N
+    const int cfg = (g.force_cfg >= 0 && g.force_cfg < kNumCfgs) ? g.force_cfg
+                                                                 : choose_cfg(ctx, g.M, g.N, g.batch);
+    const Cfg& c = kCfgs[cfg];
+
+    CUtensorMap mapA, mapB;
+    if (a_kc) make_map(ctx, &mapA, g.A, g.K, g.M, g.lda, g.batch, g.strideA, BK, c.BM);
+    else      make_map(ctx, &mapA, g.A, g.M, g.K, g.lda, g.batch, g.strideA, 16, BK);
+    if (b_kc) make_map(ctx, &mapB, g.B, g.K, g.N, g.ldb, g.batch, g.strideB, BK, c.BN);
+    else      make_map(ctx, &mapB, g.B, g.N, g.K, g.ldb, g.batch, g.strideB, 16, BK);
+
+    Params p;
+    p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
+    p.tilesM = (int)((g.M + c.BM - 1) / c.BM);
+    p.tilesN = (int)((g.N + c.BN - 1) / c.BN);
+    p.tiles_per_batch = (long long)p.tilesM * p.tilesN;
+    p.batch = (int)g.batch;
+    p.raster_n_fast = p.tilesM >= p.tilesN ? 1 : 0;
+    p.C = g.C; p.ldc = g.ldc; p.strideC = g.strideC;
+    p.alpha = g.alpha; p.beta = g.beta;
+    p.epi = EPI_NONE; p.e0 = p.e1 = nullptr; p.ei0 = p.ei1 = 0;
+    const long long total = p.tiles_per_batch * g.batch;
+    JUES_REQUIRE(total < (1ll << 31), "GEMM grid too large");
+
+    int smem = 0;
+    KernelFn fn = pick_kernel(a_kc, b_kc, cfg, &smem);
+    static std::map<void*, bool> attr_set;  // per process; kernels are per-device functions
+    if (!attr_set[(void*)fn]) {
+        JUES_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[(void*)fn] = true;
+    }
+    const int threads = (c.BM / c.WM) * (c.BN / c.WN) * 32 + 32;
+    fn<<<(unsigned)total, threads, smem, ctx->stream>>>(mapA, mapB, p);
+    JUES_CUDA(cudaGetLastError());
+    ctx->stats.gemm_flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch;
+    ctx->stats.gemm_launches += 1;
+}
+
+}  // namespace jues

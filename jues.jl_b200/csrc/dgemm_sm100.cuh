@@ -1,0 +1,283 @@
+// FP64 GEMM for sm_100a: DMMA (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4) register tiles fed by
+// TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier full/empty ring, with a
+// dedicated producer warp.  tcgen05 has no FP64 kind, so the FP64 tensor path on Blackwell is the
+// warp-level DMMA; all wider PTX f64 shapes (m16n8k4/8/16) lower to the same DMMA.8x8x4 on sm_100a.
+//
+// Operand layouts in shared memory (one pipeline stage holds a BMx16 slice of op(A) and a BNx16
+// slice of op(B)^T; BK = 16 doubles = one 128-byte swizzle row):
+//   KC ("K-contiguous": A stored KxM, i.e. transA='T'; B stored KxN, i.e. transB='N')
+//       one TMA box {16 k, R rows}; element (r,k) at  r*128 + (((k>>1) ^ (r&7))<<4) + (k&1)*8
+//   RC ("row-contiguous": A stored MxK, transA='N'; B stored NxK, transB='T')
+//       R/16 TMA boxes {16 r, 16 k} of 2 KB; element (r,k) at
+//       (r>>4)*2048 + k*128 + ((((r&15)>>1) ^ (k&7))<<4) + (r&1)*8
+// DMMA wants, from lane (g = lane>>2, t = lane&3), A[row g][k t] and B[k t][col g].  The mapping of
+// "MMA row/col g" to tile rows and of "MMA k t" to tile k is free as long as A, B and the
+// accumulator agree, and is chosen so that every LDS.64 is bank-conflict-free for BOTH layouts:
+//   k(t, s)  = 2t + ((t&1) ^ s)     s = 0,1 : the two DMMAs that cover an 8-k block
+//                                    ({0,3,4,7} and {1,2,5,6})
+//   row(g)   = g                     for an RC operand
+//   row(g)   = {0,1,4,5,2,3,6,7}[g]  for a KC operand
+// (verified exhaustively by tests/test_smem_layout.py).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace jues {
+namespace gemm {
+
+constexpr int BK = 16;  // doubles per pipeline stage along K (= 128 B)
+
+struct Params {
+    int M, N, K;
+    int tilesM, tilesN;
+    long long tiles_per_batch;
+    int batch;
+    int raster_n_fast;  // 1: consecutive CTAs walk N first (A tile shared), 0: M first
+    double* C;
+    long long ldc;
+    long long strideC;
+    double alpha, beta;
+    // optional fused epilogue (see Epi enum)
+    int epi;
+    const double* e0;  // epilogue operand 0
+    const double* e1;  // epilogue operand 1
+    int ei0, ei1;      // epilogue ints
+};
+
+enum Epi : int {
+    EPI_NONE = 0,  // C = alpha*acc + beta*C
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a mis-programmed pipeline traps (-> CUDA error on the host) instead of hanging
+// the GPU.  ~10 s at 2 GHz.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 20000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// byte offset of element (r, k) of an operand tile, r in [0,R), k in [0,16)
+template <bool KC>
+__host__ __device__ __forceinline__ int frag_off(int r, int k) {
+    if (KC) return r * 128 + ((((k >> 1) ^ (r & 7)) << 4) | ((k & 1) << 3));
+    return (r >> 4) * 2048 + k * 128 + (((((r & 15) >> 1) ^ (k & 7)) << 4) | ((r & 1) << 3));
+}
+template <bool KC>
+__host__ __device__ __forceinline__ int frag_row(int g) {  // MMA row/col g -> row inside an 8-row tile
+    if (KC) return (g & 1) | ((g & 2) << 1) | ((g & 4) >> 1);
+    return g;
+}
+__host__ __device__ __forceinline__ int frag_k(int t, int s) { return 2 * t + ((t & 1) ^ s); }
+
+template <int BM, int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * BK * 8;
+    static constexpr int B_BYTES = BN * BK * 8;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 2 * STAGES * 8 + 1024;  // + alignment slack
+};
+
+template <bool A_KC, bool B_KC, int BM, int BN, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32 + 32, 1)
+dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const Params p) {
+    constexpr int WARPS_M = BM / WM;
+    constexpr int WARPS_N = BN / WN;
+    constexpr int NCONS = WARPS_M * WARPS_N;  // consumer warps
+    constexpr int TI = WM / 8;                // 8x8 accumulator tiles per warp along M
+    constexpr int TJ = WN / 8;
+    using L = SmemLayout<BM, BN, STAGES>;
+    static_assert(WM % 16 == 0 && WN % 16 == 0, "warp tile must be a multiple of 16");
+    static_assert(BM % 16 == 0 && BN % 16 == 0 && BM <= 256 && BN <= 256, "bad CTA tile");
+
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_full = smem_base + L::BAR_OFF;
+    const uint32_t bar_empty = bar_full + STAGES * 8;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- tile coordinates -------------------------------------------------------------------
+    const long long tile = blockIdx.x;
+    const int bz = (int)(tile / p.tiles_per_batch);
+    const int rt = (int)(tile - (long long)bz * p.tiles_per_batch);
+    int tm, tn;
+    if (p.raster_n_fast) {
+        tm = rt / p.tilesN;
+        tn = rt - tm * p.tilesN;
+    } else {
+        tn = rt / p.tilesM;
+        tm = rt - tn * p.tilesM;
+    }
+    const int m0 = tm * BM;
+    const int n0 = tn * BN;
+    const int KT = (p.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, NCONS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NCONS) {
+        // ================================ TMA producer ==========================================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (uint32_t)((kt / STAGES) & 1);
+                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                const uint32_t full = bar_full + 8 * s;
+                mbar_expect_tx(full, (uint32_t)L::STAGE_BYTES);
+                const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+                const uint32_t sb = sa + L::A_BYTES;
+                const int k0 = kt * BK;
+                if (A_KC) {
+                    tma_load_3d(sa, &mapA, full, k0, m0, bz);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < BM / 16; ++q)
+                        tma_load_3d(sa + q * 2048, &mapA, full, m0 + 16 * q, k0, bz);
+                }
+                if (B_KC) {
+                    tma_load_3d(sb, &mapB, full, k0, n0, bz);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < BN / 16; ++q)
+                        tma_load_3d(sb + q * 2048, &mapB, full, n0 + 16 * q, k0, bz);
+                }
+            }
+        }
+        return;
+    }
+
+    // ================================== DMMA consumers ==========================================
+    const int wm = warp % WARPS_M;
+    const int wn = warp / WARPS_M;
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int ra = frag_row<A_KC>(g);
+    const int rb = frag_row<B_KC>(g);
+
+    // byte offsets of this lane's fragment element for (s, kb, i&1); tile i adds (i>>1)*2048
+    int offA[2][2][2], offB[2][2][2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int ip = 0; ip < 2; ++ip) {
+                const int k = kb * 8 + frag_k(t, s);
+                offA[s][kb][ip] = frag_off<A_KC>(wm * WM + ip * 8 + ra, k);
+                offB[s][kb][ip] = L::A_BYTES + frag_off<B_KC>(wn * WN + ip * 8 + rb, k);
+            }
+
+    double acc[TI][TJ][2];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (uint32_t)((kt / STAGES) & 1);
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint32_t st = smem_base + s * L::STAGE_BYTES;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+            for (int ss = 0; ss < 2; ++ss) {
+                double a[TI], b[TJ];
+#pragma unroll
+                for (int i = 0; i < TI; ++i)
+                    a[i] = lds64(st + offA[ss][kb][i & 1] + (i >> 1) * 2048);
+#pragma unroll
+                for (int j = 0; j < TJ; ++j)
+                    b[j] = lds64(st + offB[ss][kb][j & 1] + (j >> 1) * 2048);
+#pragma unroll
+                for (int i = 0; i < TI; ++i)
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    }
+
+    // ===================================== epilogue ============================================
+    double* __restrict__ Cb = p.C + (long long)bz * p.strideC;
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int j = 0; j < TJ; ++j) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int n = n0 + wn * WN + j * 8 + frag_row<B_KC>(2 * t + c);
+            if (n < p.N) {
+                double* col = Cb + (long long)n * p.ldc;
+#pragma unroll
+                for (int i = 0; i < TI; ++i) {
+                    const int m = m0 + wm * WM + i * 8 + ra;
+                    if (m < p.M) {
+                        double v = alpha * acc[i][j][c];
+                        if (beta != 0.0) v += beta * col[m];
+                        col[m] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace gemm
+}  // namespace jues

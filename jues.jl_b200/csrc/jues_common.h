@@ -1,0 +1,178 @@
+// jues_b200 -- internal common definitions (context, errors, device buffers).
+// Not part of the public C ABI (that is include/jues_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <map>
+#include <stdexcept>
+
+#include "../../include/jues_b200.h"
+
+namespace jues {
+
+// ---------------------------------------------------------------------------------------------
+// Errors: internal code throws jues::Error; the extern "C" layer catches and converts to a
+// negative status + message (no exception ever crosses the ABI).
+// ---------------------------------------------------------------------------------------------
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define JUES_CUDA(call)                                                                         \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            char buf__[512];                                                                    \
+            snprintf(buf__, sizeof buf__, "CUDA error %s (%d) at %s:%d: %s", cudaGetErrorName(e__), \
+                     (int)e__, __FILE__, __LINE__, cudaGetErrorString(e__));                    \
+            throw ::jues::Error(e__ == cudaErrorMemoryAllocation ? JUES_B200_ENOMEM             \
+                                                                 : JUES_B200_ECUDA, buf__);     \
+        }                                                                                       \
+    } while (0)
+
+#define JUES_REQUIRE(cond, msg)                                                                 \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            char buf__[512];                                                                    \
+            snprintf(buf__, sizeof buf__, "invalid argument: %s  [%s] at %s:%d", msg, #cond,    \
+                     __FILE__, __LINE__);                                                       \
+            throw ::jues::Error(JUES_B200_EINVAL, buf__);                                       \
+        }                                                                                       \
+    } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// ---------------------------------------------------------------------------------------------
+// Per-phase statistics the benchmark reads back (CUDA-event time on the library's stream,
+// floating-point operations actually issued by the GEMM kernels, launch counts).
+// ---------------------------------------------------------------------------------------------
+struct Stats {
+    double gemm_flops = 0;       // 2*M*N*K*batch summed over launches (padded dims)
+    long long gemm_launches = 0;
+    long long aux_launches = 0;  // permute / elementwise / reduction kernels
+    void reset() { *this = Stats(); }
+};
+
+}  // namespace jues
+
+// The opaque context of the C ABI.
+struct jues_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    jues::PFN_encodeTiled encode = nullptr;
+    std::string last_error;
+    jues::Stats stats;
+    // scratch for device-side reductions (partials) and small host mirror
+    double* red_dev = nullptr;   // [red_cap]
+    double* red_host = nullptr;  // pinned, [red_cap]
+    size_t red_cap = 0;
+    // timing records: name -> milliseconds (accumulated), filled by Timer
+    std::vector<std::pair<std::string, float>> timings;
+    size_t bytes_allocated = 0;
+    size_t bytes_peak = 0;
+    // multi-GPU (one process per GPU): rank / world size and an NCCL communicator (opaque here)
+    int rank = 0;
+    int nranks = 1;
+    void* nccl_comm = nullptr;
+    void* nccl_lib = nullptr;
+};
+
+namespace jues {
+
+// ---------------------------------------------------------------------------------------------
+// Device buffer with RAII; all allocations go through the context for accounting.
+// ---------------------------------------------------------------------------------------------
+struct DBuf {
+    jues_ctx* ctx = nullptr;
+    double* p = nullptr;
+    size_t n = 0;  // elements
+    DBuf() {}
+    DBuf(jues_ctx* c, size_t n_) { alloc(c, n_); }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept { *this = std::move(o); }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            ctx = o.ctx; p = o.p; n = o.n;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    ~DBuf() { release(); }
+    void alloc(jues_ctx* c, size_t n_) {
+        release();
+        ctx = c;
+        n = n_;
+        size_t bytes = (n_ ? n_ : 1) * sizeof(double);
+        // keep every allocation a multiple of 256 B so that TMA boxes that overhang the logical
+        // end of a tensor never leave the allocation's page
+        bytes = (bytes + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            char buf[256];
+            snprintf(buf, sizeof buf, "device allocation of %.3f GB failed (%s); %.3f GB already held",
+                     bytes / 1e9, cudaGetErrorString(e), c->bytes_allocated / 1e9);
+            cudaGetLastError();
+            throw Error(JUES_B200_ENOMEM, buf);
+        }
+        c->bytes_allocated += bytes;
+        if (c->bytes_allocated > c->bytes_peak) c->bytes_peak = c->bytes_allocated;
+    }
+    void release() {
+        if (p) {
+            size_t bytes = (n ? n : 1) * sizeof(double);
+            bytes = (bytes + 255) & ~size_t(255);
+            cudaFree(p);
+            if (ctx) ctx->bytes_allocated -= bytes;
+            p = nullptr;
+            n = 0;
+        }
+    }
+    void zero() { JUES_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream)); }
+};
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// CUDA-event timer writing into ctx->timings.
+struct Timer {
+    jues_ctx* ctx;
+    std::string name;
+    cudaEvent_t e0, e1;
+    bool open = true;
+    Timer(jues_ctx* c, const std::string& n) : ctx(c), name(n) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, c->stream);
+    }
+    float stop() {
+        float ms = 0;
+        if (open) {
+            cudaEventRecord(e1, ctx->stream);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+            ctx->timings.emplace_back(name, ms);
+            open = false;
+        }
+        return ms;
+    }
+    ~Timer() {
+        stop();
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+};
+
+}  // namespace jues
