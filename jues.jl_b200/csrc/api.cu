@@ -1,0 +1,363 @@
+// extern "C" entry points for the transformation, RMP2, RCCD, RCCSD and the device-resident
+// rank-4 tensor handle (include/jues_b200.h).
+#include "api_util.h"
+#include "cc.h"
+
+#include <memory>
+
+using namespace jues;
+
+namespace {
+
+void begin_call(jues_ctx* ctx) {
+    ctx->timings.clear();
+    ctx->stats.reset();
+    ctx->bytes_peak = ctx->bytes_allocated;
+}
+
+size_t free_device_bytes() {
+    size_t f = 0, t = 0;
+    cudaMemGetInfo(&f, &t);
+    return f;
+}
+
+// A GaoSource for a host tensor: resident copy when it fits comfortably, streamed otherwise.
+struct HostGaoHolder {
+    DBuf dense;
+    std::unique_ptr<GaoSource> src;
+};
+
+void make_host_gao(jues_ctx* ctx, HostGaoHolder& h, const double* gao, int64_t nao, bool need_resident) {
+    JUES_REQUIRE(gao != nullptr && nao > 0, "null or empty gao");
+    const int64_t np = round_up(nao, 2);
+    const double bytes = (double)np * np * np * np * 8.0;
+    const double avail = (double)free_device_bytes() + 0.0;
+    const bool force_stream = getenv("JUES_B200_FORCE_STREAM") != nullptr;  // testing hook
+    if (need_resident || (!force_stream && bytes < 0.45 * avail)) {
+        Timer t(ctx, "h2d.gao");
+        h.dense.alloc(ctx, (size_t)(np * np * np * np));
+        upload_padded_gao(ctx, h.dense.p, gao, nao, np);
+        h.src.reset(new DeviceGao(h.dense.p, nao, np));
+    } else {
+        h.src.reset(new HostGao(gao, nao, np));
+    }
+}
+
+void check_t4_is_gao(const jues_t4* g) {
+    JUES_REQUIRE(g && g->p, "null tensor handle");
+    JUES_REQUIRE(g->d[0] == g->d[1] && g->d[1] == g->d[2] && g->d[2] == g->d[3],
+                 "gao handle must be (nao,nao,nao,nao)");
+}
+
+// download a padded device tensor (dp) into an unpadded host array (d)
+void download_block(jues_ctx* ctx, const double* dev, const int64_t dp[4], double* host, const int64_t d[4]) {
+    const size_t n = (size_t)(d[0] * d[1] * d[2] * d[3]);
+    if (!n) return;
+    if (d[0] == dp[0] && d[1] == dp[1] && d[2] == dp[2]) {
+        JUES_CUDA(cudaMemcpyAsync(host, dev, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        DBuf tmp(ctx, n);
+        block_copy(ctx, dev, dp, tmp.p, d, d);
+        JUES_CUDA(cudaMemcpyAsync(host, tmp.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+void transform_common(jues_ctx* ctx, GaoSource& src, const double* const Ch[4], const int64_t d[4],
+                      int phys_order, DBuf& out, int64_t dp_out[4]) {
+    const int64_t nao = src.n, np = src.np;
+    DBuf Cd[4];
+    const double* Cm[4];
+    int64_t dp[4];
+    for (int q = 0; q < 4; ++q) {
+        JUES_REQUIRE(Ch[q] != nullptr && d[q] > 0, "null or empty coefficient matrix");
+        dp[q] = round_up(d[q], 2);
+        upload_padded_matrix(ctx, Cd[q], Ch[q], nao, d[q], np, dp[q]);
+        Cm[q] = Cd[q].p;
+    }
+    const size_t n = (size_t)(dp[0] * dp[1] * dp[2] * dp[3]);
+    DBuf chem(ctx, n);
+    {
+        Timer t(ctx, "tei.transform");
+        tei_transform_dev(ctx, src, Cm, dp, chem.p);
+    }
+    if (phys_order) {
+        Timer t(ctx, "tei.permute");
+        out.alloc(ctx, n);
+        Ten a(chem.p, dp[0], dp[1], dp[2], dp[3]), b(out.p, dp[0], dp[2], dp[1], dp[3]);
+        permute_axpby(ctx, 1.0, a, "iajb", 0.0, b, "ijab");
+        dp_out[0] = dp[0]; dp_out[1] = dp[2]; dp_out[2] = dp[1]; dp_out[3] = dp[3];
+    } else {
+        out = std::move(chem);
+        for (int q = 0; q < 4; ++q) dp_out[q] = dp[q];
+    }
+}
+
+}  // namespace
+
+extern "C" int jues_b200_set_amplitude_callback(jues_ctx* ctx, jues_b200_amp_cb cb, void* user) {
+    if (!ctx) return JUES_B200_EINVAL;
+    ctx->amp_cb = cb;
+    ctx->amp_user = user;
+    return JUES_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tei_transform
+// ---------------------------------------------------------------------------------------------
+extern "C" int jues_b200_tei_transform(jues_ctx* ctx, const double* gao, int64_t nao, const double* C1,
+                                       int64_t d1, const double* C2, int64_t d2, const double* C3,
+                                       int64_t d3, const double* C4, int64_t d4, int phys_order, double* out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    JUES_REQUIRE(out != nullptr, "null output");
+    Timer total(ctx, "total");
+    HostGaoHolder h;
+    make_host_gao(ctx, h, gao, nao, false);
+    const double* Ch[4] = {C1, C2, C3, C4};
+    const int64_t d[4] = {d1, d2, d3, d4};
+    DBuf res;
+    int64_t dp[4];
+    transform_common(ctx, *h.src, Ch, d, phys_order, res, dp);
+    const int64_t dl[4] = {d1, phys_order ? d3 : d2, phys_order ? d2 : d3, d4};
+    Timer t(ctx, "d2h.out");
+    download_block(ctx, res.p, dp, out, dl);
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_tei_transform_t4(jues_ctx* ctx, const jues_t4* gao, const double* C1, int64_t d1,
+                                          const double* C2, int64_t d2, const double* C3, int64_t d3,
+                                          const double* C4, int64_t d4, int phys_order, jues_t4** out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    check_t4_is_gao(gao);
+    JUES_REQUIRE(out != nullptr, "null output");
+    Timer total(ctx, "total");
+    DeviceGao src(gao->p, gao->d[0], gao->dp[0]);
+    const double* Ch[4] = {C1, C2, C3, C4};
+    const int64_t d[4] = {d1, d2, d3, d4};
+    DBuf res;
+    int64_t dp[4];
+    transform_common(ctx, src, Ch, d, phys_order, res, dp);
+    const int64_t dl[4] = {d1, phys_order ? d3 : d2, phys_order ? d2 : d3, d4};
+    jues_t4* t = nullptr;
+    int rc = jues_b200_t4_create(ctx, dl[0], dl[1], dl[2], dl[3], &t);
+    if (rc) return rc;
+    JUES_CUDA(cudaMemcpyAsync(t->p, res.p, (size_t)(dp[0] * dp[1] * dp[2] * dp[3]) * 8,
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = t;
+    JUES_API_END(ctx)
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMP2
+// ---------------------------------------------------------------------------------------------
+extern "C" int jues_b200_rmp2(jues_ctx* ctx, const double* gao, int64_t nao, const double* Cao, int64_t nocc,
+                              const double* Cav, int64_t nvir, const double* eps, double* e_mp2) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    JUES_REQUIRE(e_mp2 != nullptr, "null output");
+    Timer total(ctx, "total");
+    Problem P;
+    setup_problem(ctx, P, nao, Cao, nocc, Cav, nvir, eps);
+    HostGaoHolder h;
+    make_host_gao(ctx, h, gao, nao, false);
+    *e_mp2 = rmp2_dev(ctx, P, *h.src);
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_rmp2_t4(jues_ctx* ctx, const jues_t4* gao, const double* Cao, int64_t nocc,
+                                 const double* Cav, int64_t nvir, const double* eps, double* e_mp2) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    check_t4_is_gao(gao);
+    JUES_REQUIRE(e_mp2 != nullptr, "null output");
+    Timer total(ctx, "total");
+    Problem P;
+    setup_problem(ctx, P, gao->d[0], Cao, nocc, Cav, nvir, eps);
+    DeviceGao src(gao->p, gao->d[0], gao->dp[0]);
+    *e_mp2 = rmp2_dev(ctx, P, src);
+    JUES_API_END(ctx)
+}
+
+// ---------------------------------------------------------------------------------------------
+// RCCD / RCCSD
+// ---------------------------------------------------------------------------------------------
+namespace {
+void run_cc(jues_ctx* ctx, GaoSource& src, const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+            const double* eps, bool singles, int maxit, int guess_mode, double* e, double* e_hist,
+            double* T1_out, double* T2_out) {
+    JUES_REQUIRE(e != nullptr, "null energy output");
+    Problem P;
+    setup_problem(ctx, P, src.n, Cao, nocc, Cav, nvir, eps);
+    CCResult r = cc_dev(ctx, P, src, singles, maxit, guess_mode, T1_out, T2_out, ctx->amp_cb, ctx->amp_user);
+    *e = r.energy;
+    if (e_hist)
+        for (int k = 0; k <= maxit; ++k) e_hist[k] = r.e_hist[k];
+}
+}  // namespace
+
+extern "C" int jues_b200_rccd(jues_ctx* ctx, const double* gao, int64_t nao, const double* Cao, int64_t nocc,
+                              const double* Cav, int64_t nvir, const double* eps, int maxit, int guess_mode,
+                              double* e_ccd, double* e_hist, double* T2_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    JUES_REQUIRE(guess_mode == 0 || guess_mode == 1, "guess_mode must be 0 (reference) or 1 (MP2)");
+    Timer total(ctx, "total");
+    HostGaoHolder h;
+    make_host_gao(ctx, h, gao, nao, true);
+    run_cc(ctx, *h.src, Cao, nocc, Cav, nvir, eps, false, maxit, guess_mode, e_ccd, e_hist, nullptr, T2_out);
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_rccd_t4(jues_ctx* ctx, const jues_t4* gao, const double* Cao, int64_t nocc,
+                                 const double* Cav, int64_t nvir, const double* eps, int maxit,
+                                 int guess_mode, double* e_ccd, double* e_hist, double* T2_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    check_t4_is_gao(gao);
+    JUES_REQUIRE(guess_mode == 0 || guess_mode == 1, "guess_mode must be 0 (reference) or 1 (MP2)");
+    Timer total(ctx, "total");
+    DeviceGao src(gao->p, gao->d[0], gao->dp[0]);
+    run_cc(ctx, src, Cao, nocc, Cav, nvir, eps, false, maxit, guess_mode, e_ccd, e_hist, nullptr, T2_out);
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_rccsd(jues_ctx* ctx, const double* gao, int64_t nao, const double* Cao, int64_t nocc,
+                               const double* Cav, int64_t nvir, const double* eps, int maxit, double* e_ccsd,
+                               double* e_hist, double* T1_out, double* T2_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    Timer total(ctx, "total");
+    HostGaoHolder h;
+    make_host_gao(ctx, h, gao, nao, true);
+    run_cc(ctx, *h.src, Cao, nocc, Cav, nvir, eps, true, maxit, 1, e_ccsd, e_hist, T1_out, T2_out);
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_rccsd_t4(jues_ctx* ctx, const jues_t4* gao, const double* Cao, int64_t nocc,
+                                  const double* Cav, int64_t nvir, const double* eps, int maxit,
+                                  double* e_ccsd, double* e_hist, double* T1_out, double* T2_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    check_t4_is_gao(gao);
+    Timer total(ctx, "total");
+    DeviceGao src(gao->p, gao->d[0], gao->dp[0]);
+    run_cc(ctx, src, Cao, nocc, Cav, nvir, eps, true, maxit, 1, e_ccsd, e_hist, T1_out, T2_out);
+    JUES_API_END(ctx)
+}
+
+// ---------------------------------------------------------------------------------------------
+// jues_t4: device-resident rank-4 tensor (DiskFourTensor replacement, DiskFourTensors.jl:5-95)
+// ---------------------------------------------------------------------------------------------
+extern "C" int jues_b200_t4_create(jues_ctx* ctx, int64_t d1, int64_t d2, int64_t d3, int64_t d4, jues_t4** out) {
+    JUES_API_BEGIN(ctx)
+    JUES_REQUIRE(out != nullptr, "null output");
+    JUES_REQUIRE(d1 > 0 && d2 > 0 && d3 > 0 && d4 > 0, "extents must be positive");
+    std::unique_ptr<jues_t4> t(new jues_t4());
+    t->ctx = ctx;
+    const int64_t d[4] = {d1, d2, d3, d4};
+    size_t n = 1;
+    for (int q = 0; q < 4; ++q) { t->d[q] = d[q]; t->dp[q] = round_up(d[q], 2); n *= (size_t)t->dp[q]; }
+    t->bytes = (n * 8 + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&t->p, t->bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        char buf[160];
+        snprintf(buf, sizeof buf, "device allocation of %.3f GB for a rank-4 tensor failed", t->bytes / 1e9);
+        throw Error(JUES_B200_ENOMEM, buf);
+    }
+    JUES_CUDA(cudaMemsetAsync(t->p, 0, t->bytes, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = t.release();
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_t4_destroy(jues_t4* t) {
+    if (!t) return JUES_B200_EINVAL;
+    if (t->ctx) cudaSetDevice(t->ctx->device);
+    if (t->p) cudaFree(t->p);
+    delete t;
+    return JUES_B200_OK;
+}
+
+extern "C" int jues_b200_t4_dims(const jues_t4* t, int64_t dims_out[4]) {
+    if (!t || !dims_out) return JUES_B200_EINVAL;
+    for (int q = 0; q < 4; ++q) dims_out[q] = t->d[q];
+    return JUES_B200_OK;
+}
+
+extern "C" int jues_b200_t4_fill(jues_t4* t, double value) {
+    if (!t) return JUES_B200_EINVAL;
+    jues_ctx* ctx = t->ctx;
+    JUES_API_BEGIN(ctx)
+    // pads stay zero: fill the logical block only
+    const size_t n = (size_t)(t->dp[0] * t->dp[1] * t->dp[2] * t->dp[3]);
+    if (t->d[0] == t->dp[0] && t->d[1] == t->dp[1] && t->d[2] == t->dp[2] && t->d[3] == t->dp[3]) {
+        fill(ctx, t->p, n, value);
+    } else {
+        const size_t nl = (size_t)(t->d[0] * t->d[1] * t->d[2] * t->d[3]);
+        DBuf tmp(ctx, nl);
+        fill(ctx, tmp.p, nl, value);
+        block_copy(ctx, tmp.p, t->d, t->p, t->dp, t->d);
+    }
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    JUES_API_END(ctx)
+}
+
+namespace {
+void check_range(const jues_t4* t, const int64_t lo[4], const int64_t hi[4], int64_t ext[4]) {
+    JUES_REQUIRE(t && t->p && lo && hi, "null argument");
+    for (int q = 0; q < 4; ++q) {
+        JUES_REQUIRE(lo[q] >= 0 && hi[q] <= t->d[q] && lo[q] <= hi[q], "slice out of range");
+        ext[q] = hi[q] - lo[q];
+    }
+}
+}  // namespace
+
+extern "C" int jues_b200_t4_set_slice(jues_t4* t, const int64_t lo[4], const int64_t hi[4], const double* host) {
+    if (!t) return JUES_B200_EINVAL;
+    jues_ctx* ctx = t->ctx;
+    JUES_API_BEGIN(ctx)
+    int64_t ext[4];
+    check_range(t, lo, hi, ext);
+    JUES_REQUIRE(host != nullptr, "null host buffer");
+    const size_t n = (size_t)(ext[0] * ext[1] * ext[2] * ext[3]);
+    if (n) {
+        DBuf tmp(ctx, n);
+        JUES_CUDA(cudaMemcpyAsync(tmp.p, host, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        double* dst = t->p + lo[0] + t->dp[0] * (lo[1] + t->dp[1] * (lo[2] + t->dp[2] * lo[3]));
+        block_copy(ctx, tmp.p, ext, dst, t->dp, ext);
+        JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_t4_get_slice(const jues_t4* t, const int64_t lo[4], const int64_t hi[4], double* host) {
+    if (!t) return JUES_B200_EINVAL;
+    jues_ctx* ctx = t->ctx;
+    JUES_API_BEGIN(ctx)
+    int64_t ext[4];
+    check_range(t, lo, hi, ext);
+    JUES_REQUIRE(host != nullptr, "null host buffer");
+    const size_t n = (size_t)(ext[0] * ext[1] * ext[2] * ext[3]);
+    if (n) {
+        DBuf tmp(ctx, n);
+        const double* src = t->p + lo[0] + t->dp[0] * (lo[1] + t->dp[1] * (lo[2] + t->dp[2] * lo[3]));
+        block_copy(ctx, src, t->dp, tmp.p, ext, ext);
+        JUES_CUDA(cudaMemcpyAsync(host, tmp.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_t4_synth_eri(jues_t4* t, uint64_t seed, double scale) {
+    if (!t) return JUES_B200_EINVAL;
+    jues_ctx* ctx = t->ctx;
+    JUES_API_BEGIN(ctx)
+    check_t4_is_gao(t);
+    synth_eri_fill(ctx, t->p, t->d[0], t->dp[0], 0, t->dp[3], seed, scale);
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    JUES_API_END(ctx)
+}

@@ -41,6 +41,12 @@ extern "C" int jues_b200_init(jues_ctx** out, int device) {
         ctx->device = device;
         ctx->sm_count = prop.multiProcessorCount;
         JUES_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        {   // keep freed blocks in the stream-ordered pool (all work of a context is on one stream)
+            cudaMemPool_t pool;
+            JUES_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+            unsigned long long thr = ~0ull;
+            JUES_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        }
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         JUES_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));

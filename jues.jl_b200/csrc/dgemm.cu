@@ -1,7 +1,10 @@
 // Host launcher of the sm_100a TMA + DMMA FP64 GEMM: builds the TMA tensor maps, picks a tile
 // configuration, launches on the context's stream.
 #include "dgemm.h"
+#include <algorithm>
+#include <cmath>
 #include "dgemm_sm100.cuh"
+#include "tensor_ops.h"
 
 namespace jues {
 
@@ -65,21 +68,35 @@ void make_map(jues_ctx* ctx, CUtensorMap* map, const double* base, int64_t d0, i
     }
 }
 
-int choose_cfg(jues_ctx* ctx, int64_t M, int64_t N, int64_t batch) {
-    int best = 0;
+// Pick the tile configuration and split-K factor that minimise a simple time model:
+// waves(tiles*split / SMs) * (stages per CTA + fixed prologue/epilogue cost) * tile cost.
+void choose_cfg(jues_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t batch, bool allow_split,
+                int* cfg_out, int* split_out) {
+    int best = 0, best_split = 1;
     double best_t = 1e300;
     const double sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    const int KT = (int)((K + BK - 1) / BK);
     for (int c = 0; c < kNumCfgs; ++c) {
         const double tiles = (double)((M + kCfgs[c].BM - 1) / kCfgs[c].BM) *
                              (double)((N + kCfgs[c].BN - 1) / kCfgs[c].BN) * (double)batch;
-        const double waves = ceil(tiles / sms);
-        const double t = waves * kCfgs[c].BM * kCfgs[c].BN * kCfgs[c].cost;
-        if (t < best_t * 0.999) {
-            best_t = t;
-            best = c;
+        int max_split = 1;
+        if (allow_split && tiles < sms) max_split = (int)std::min<double>(64.0, std::max(1.0, KT / 8.0));
+        for (int sp = 1; sp <= max_split; sp = sp < 4 ? sp + 1 : sp * 2) {
+            const int ktp = (KT + sp - 1) / sp;
+            const double waves = ceil(tiles * sp / sms);
+            // per-CTA cost in "k-stage" units: mainloop stages + ~6 stages of prologue/epilogue,
+            // plus the reduction pass over the split workspace
+            double t = waves * (ktp + 6.0) * kCfgs[c].BM * kCfgs[c].BN * kCfgs[c].cost;
+            if (sp > 1) t += 0.05 * sp * (double)M * (double)N * (double)batch / sms * 16.0;
+            if (t < best_t * 0.999) {
+                best_t = t;
+                best = c;
+                best_split = sp;
+            }
         }
     }
-    return best;
+    *cfg_out = best;
+    *split_out = best_split;
 }
 
 }  // namespace
@@ -95,15 +112,26 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
     JUES_REQUIRE(g.ldc >= g.M, "GEMM ldc < M");
     const bool a_kc = g.transA;   // A stored K x M
     const bool b_kc = !g.transB;  // B stored K x N
-    const int cfg = (g.force_cfg >= 0 && g.force_cfg < kNumCfgs) ? g.force_cfg
-                                                                 : choose_cfg(ctx, g.M, g.N, g.batch);
+    int cfg = 0, ksplit = 1;
+    choose_cfg(ctx, g.M, g.N, g.K, g.batch, true, &cfg, &ksplit);
+    if (g.force_cfg >= 0) {
+        cfg = g.force_cfg % kNumCfgs;
+        if (g.force_cfg >= kNumCfgs) ksplit = g.force_cfg / kNumCfgs + 1;  // testing: cfg + 4*(split-1)
+    }
     const Cfg& c = kCfgs[cfg];
+    const int KT_all = (int)((g.K + BK - 1) / BK);
+    if (ksplit > KT_all) ksplit = KT_all;
+    int kt_per_split = (KT_all + ksplit - 1) / ksplit;
+    ksplit = (KT_all + kt_per_split - 1) / kt_per_split;  // no empty splits
 
     CUtensorMap mapA, mapB;
-    if (a_kc) make_map(ctx, &mapA, g.A, g.K, g.M, g.lda, g.batch, g.strideA, BK, c.BM);
-    else      make_map(ctx, &mapA, g.A, g.M, g.K, g.lda, g.batch, g.strideA, 16, BK);
-    if (b_kc) make_map(ctx, &mapB, g.B, g.K, g.N, g.ldb, g.batch, g.strideB, BK, c.BN);
-    else      make_map(ctx, &mapB, g.B, g.N, g.K, g.ldb, g.batch, g.strideB, 16, BK);
+    const int bmulA = (g.batch > 1 && g.strideA != 0) ? 1 : 0;
+    const int bmulB = (g.batch > 1 && g.strideB != 0) ? 1 : 0;
+    const int64_t nbA = bmulA ? g.batch : 1, nbB = bmulB ? g.batch : 1;
+    if (a_kc) make_map(ctx, &mapA, g.A, g.K, g.M, g.lda, nbA, g.strideA, BK, c.BM);
+    else      make_map(ctx, &mapA, g.A, g.M, g.K, g.lda, nbA, g.strideA, 16, BK);
+    if (b_kc) make_map(ctx, &mapB, g.B, g.K, g.N, g.ldb, nbB, g.strideB, BK, c.BN);
+    else      make_map(ctx, &mapB, g.B, g.N, g.K, g.ldb, nbB, g.strideB, 16, BK);
 
     Params p;
     p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
@@ -111,11 +139,23 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
     p.tilesN = (int)((g.N + c.BN - 1) / c.BN);
     p.tiles_per_batch = (long long)p.tilesM * p.tilesN;
     p.batch = (int)g.batch;
+    p.ksplit = ksplit;
+    p.bmulA = bmulA; p.bmulB = bmulB;
+    p.kt_per_split = kt_per_split;
     p.raster_n_fast = p.tilesM >= p.tilesN ? 1 : 0;
-    p.C = g.C; p.ldc = g.ldc; p.strideC = g.strideC;
-    p.alpha = g.alpha; p.beta = g.beta;
+    DBuf work;
+    if (ksplit > 1) {
+        // each split writes its own dense M x N slice; a second kernel sums the slices in a fixed
+        // order (deterministic) and applies alpha/beta
+        work.alloc(ctx, (size_t)g.M * g.N * ksplit * g.batch);
+        p.C = work.p; p.ldc = g.M; p.strideSplit = g.M * g.N; p.strideC = g.M * g.N * ksplit;
+        p.alpha = 1.0; p.beta = 0.0;
+    } else {
+        p.C = g.C; p.ldc = g.ldc; p.strideC = g.strideC; p.strideSplit = 0;
+        p.alpha = g.alpha; p.beta = g.beta;
+    }
     p.epi = EPI_NONE; p.e0 = p.e1 = nullptr; p.ei0 = p.ei1 = 0;
-    const long long total = p.tiles_per_batch * g.batch;
+    const long long total = p.tiles_per_batch * g.batch * ksplit;
     JUES_REQUIRE(total < (1ll << 31), "GEMM grid too large");
 
     int smem = 0;
@@ -130,6 +170,8 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
     JUES_CUDA(cudaGetLastError());
     ctx->stats.gemm_flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch;
     ctx->stats.gemm_launches += 1;
+    if (ksplit > 1)
+        splitk_reduce(ctx, work.p, ksplit, g.M, g.N, g.batch, g.alpha, g.beta, g.C, g.ldc, g.strideC);
 }
 
 }  // namespace jues

@@ -33,6 +33,10 @@ struct Params {
     int tilesM, tilesN;
     long long tiles_per_batch;
     int batch;
+    int ksplit;         // split-K factor (1 = off); split z handles k-stages [z*kt_per_split, ...)
+    int kt_per_split;
+    long long strideSplit;  // element stride between split slices of C (workspace) when ksplit > 1
+    int bmulA, bmulB;   // 0: operand is shared by all batches (batch stride 0), 1: batched
     int raster_n_fast;  // 1: consecutive CTAs walk N first (A tile shared), 0: M first
     double* C;
     long long ldc;
@@ -146,8 +150,10 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     // ---- tile coordinates -------------------------------------------------------------------
     const long long tile = blockIdx.x;
-    const int bz = (int)(tile / p.tiles_per_batch);
-    const int rt = (int)(tile - (long long)bz * p.tiles_per_batch);
+    const long long bzs = tile / p.tiles_per_batch;  // batch * ksplit + split
+    const int rt = (int)(tile - bzs * p.tiles_per_batch);
+    const int bz = (int)(bzs / p.ksplit);
+    const int zs = (int)(bzs - (long long)bz * p.ksplit);
     int tm, tn;
     if (p.raster_n_fast) {
         tm = rt / p.tilesN;
@@ -158,7 +164,9 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     const int m0 = tm * BM;
     const int n0 = tn * BN;
-    const int KT = (p.K + BK - 1) / BK;
+    const int KT_all = (p.K + BK - 1) / BK;
+    const int kt_begin = zs * p.kt_per_split;
+    const int KT = min(KT_all - kt_begin, p.kt_per_split);  // stages this CTA runs (may be <= 0)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -182,20 +190,20 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_expect_tx(full, (uint32_t)L::STAGE_BYTES);
                 const uint32_t sa = smem_base + s * L::STAGE_BYTES;
                 const uint32_t sb = sa + L::A_BYTES;
-                const int k0 = kt * BK;
+                const int k0 = (kt_begin + kt) * BK;
                 if (A_KC) {
-                    tma_load_3d(sa, &mapA, full, k0, m0, bz);
+                    tma_load_3d(sa, &mapA, full, k0, m0, bz * p.bmulA);
                 } else {
 #pragma unroll
                     for (int q = 0; q < BM / 16; ++q)
-                        tma_load_3d(sa + q * 2048, &mapA, full, m0 + 16 * q, k0, bz);
+                        tma_load_3d(sa + q * 2048, &mapA, full, m0 + 16 * q, k0, bz * p.bmulA);
                 }
                 if (B_KC) {
-                    tma_load_3d(sb, &mapB, full, k0, n0, bz);
+                    tma_load_3d(sb, &mapB, full, k0, n0, bz * p.bmulB);
                 } else {
 #pragma unroll
                     for (int q = 0; q < BN / 16; ++q)
-                        tma_load_3d(sb + q * 2048, &mapB, full, n0 + 16 * q, k0, bz);
+                        tma_load_3d(sb + q * 2048, &mapB, full, n0 + 16 * q, k0, bz * p.bmulB);
                 }
             }
         }
@@ -256,7 +264,7 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 
     // ===================================== epilogue ============================================
-    double* __restrict__ Cb = p.C + (long long)bz * p.strideC;
+    double* __restrict__ Cb = p.C + (long long)bz * p.strideC + (long long)zs * p.strideSplit;
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
     for (int j = 0; j < TJ; ++j) {

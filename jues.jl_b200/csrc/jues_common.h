@@ -86,6 +86,18 @@ struct jues_ctx {
     int nranks = 1;
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
+    // per-sweep amplitude capture (tests)
+    jues_b200_amp_cb amp_cb = nullptr;
+    void* amp_user = nullptr;
+};
+
+// device-resident rank-4 tensor handle of the C ABI (DiskFourTensor replacement)
+struct jues_t4 {
+    jues_ctx* ctx = nullptr;
+    int64_t d[4] = {0, 0, 0, 0};   // logical extents
+    int64_t dp[4] = {0, 0, 0, 0};  // padded (even) extents of the device allocation
+    double* p = nullptr;
+    size_t bytes = 0;
 };
 
 namespace jues {
@@ -119,7 +131,7 @@ struct DBuf {
         // keep every allocation a multiple of 256 B so that TMA boxes that overhang the logical
         // end of a tensor never leave the allocation's page
         bytes = (bytes + 255) & ~size_t(255);
-        cudaError_t e = cudaMalloc(&p, bytes);
+        cudaError_t e = cudaMallocAsync((void**)&p, bytes, c->stream);  // stream-ordered pool: no device sync
         if (e != cudaSuccess) {
             p = nullptr;
             char buf[256];
@@ -135,7 +147,7 @@ struct DBuf {
         if (p) {
             size_t bytes = (n ? n : 1) * sizeof(double);
             bytes = (bytes + 255) & ~size_t(255);
-            cudaFree(p);
+            cudaFreeAsync(p, ctx->stream);
             if (ctx) ctx->bytes_allocated -= bytes;
             p = nullptr;
             n = 0;

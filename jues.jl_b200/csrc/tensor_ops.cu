@@ -1,10 +1,13 @@
-// Element-wise, permutation and reduction kernels (HBM-bound side of the path).
+// Element-wise, permutation and reduction kernels: the HBM-bound side of the path (index
+// permutations, orbital-energy denominators, tau = T2 + t(x)t, energy reductions, split-K
+// epilogue, synthetic ERI generator).  All reductions are deterministic (fixed two-pass tree).
 #include "tensor_ops.h"
 #include "api_util.h"
 
 namespace jues {
 
 namespace {
+
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
     unsigned long long z = x;
@@ -21,6 +24,302 @@ __global__ void fill_pattern_kernel(double* __restrict__ p, size_t n, unsigned l
         p[i] = 2.0 * ((double)(h >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
     }
 }
+
+__global__ void fill_kernel(double* __restrict__ p, size_t n, double v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+__global__ void axpby_kernel(size_t n, double a, const double* __restrict__ x, double b,
+                             double* __restrict__ y) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (b == 0.0) {
+        for (; i < n; i += stride) y[i] = a * x[i];
+    } else {
+        for (; i < n; i += stride) y[i] = a * x[i] + b * y[i];
+    }
+}
+
+__global__ void lincomb2_kernel(size_t n, double a, const double* __restrict__ x1, double b,
+                                const double* __restrict__ x2, double* __restrict__ y) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] = a * x1[i] + b * x2[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// permutation
+// ---------------------------------------------------------------------------------------------
+struct PermArgs {
+    long long n[4];     // extents, in OUTPUT axis order
+    long long sin[4];   // input stride of each output axis
+    long long total;
+    double alpha, beta;
+};
+
+// output-fastest axis is also input-fastest (sin[0] == 1): straight coalesced copy
+__global__ void permute_same_fast(const double* __restrict__ in, double* __restrict__ out, PermArgs a) {
+    long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; L < a.total; L += stride) {
+        long long r = L;
+        const long long i0 = r % a.n[0]; r /= a.n[0];
+        const long long i1 = r % a.n[1]; r /= a.n[1];
+        const long long i2 = r % a.n[2]; r /= a.n[2];
+        const long long i3 = r;
+        const double v = a.alpha * in[i0 * a.sin[0] + i1 * a.sin[1] + i2 * a.sin[2] + i3 * a.sin[3]];
+        out[L] = (a.beta == 0.0) ? v : v + a.beta * out[L];
+    }
+}
+
+// general case: 32x32 shared-memory tile transpose between the input-fastest axis (output axis
+// `qr`) and the output-fastest axis (axis 0); the other two output axes are looped per block.
+struct PermT {
+    long long nc, nr, nu, nw;          // extents: c = out axis 0, r = input-fastest axis, u, w others
+    long long sin_c, sin_u, sin_w;     // input strides (input stride of r is 1)
+    long long sout_r, sout_u, sout_w;  // output strides (output stride of c is 1)
+    long long tiles_c, tiles_r;
+    double alpha, beta;
+};
+
+__global__ void permute_tiled(const double* __restrict__ in, double* __restrict__ out, PermT a) {
+    __shared__ double tile[32][33];
+    long long b = blockIdx.x;
+    const long long tc = b % a.tiles_c; b /= a.tiles_c;
+    const long long tr = b % a.tiles_r; b /= a.tiles_r;
+    const long long u = b % a.nu;
+    const long long w = b / a.nu;
+    const long long in_base = u * a.sin_u + w * a.sin_w;
+    const long long out_base = u * a.sout_u + w * a.sout_w;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    // load: x runs along r (input-contiguous), y along c
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const long long r = tr * 32 + tx, c = tc * 32 + ty + k;
+        if (r < a.nr && c < a.nc) tile[ty + k][tx] = in[in_base + r + c * a.sin_c];
+    }
+    __syncthreads();
+    // store: x runs along c (output-contiguous), y along r
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const long long c = tc * 32 + tx, r = tr * 32 + ty + k;
+        if (r < a.nr && c < a.nc) {
+            const long long o = out_base + c + r * a.sout_r;
+            const double v = a.alpha * tile[tx][ty + k];
+            out[o] = (a.beta == 0.0) ? v : v + a.beta * out[o];
+        }
+    }
+}
+
+__global__ void splitk_reduce_kernel(const double* __restrict__ W, int nsplit, long long M, long long N,
+                                     long long batch, double alpha, double beta, double* __restrict__ C,
+                                     long long ldc, long long strideC) {
+    const long long mn = M * N;
+    const long long total = mn * batch;
+    long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; L < total; L += stride) {
+        const long long b = L / mn;
+        const long long e = L - b * mn;
+        const long long n = e / M, m = e - n * M;
+        const double* w = W + b * (long long)nsplit * mn + e;
+        double s = 0.0;
+        for (int z = 0; z < nsplit; ++z) s += w[(long long)z * mn];
+        double* c = C + b * strideC + n * ldc + m;
+        *c = (beta == 0.0) ? alpha * s : alpha * s + beta * *c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// amplitude helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void tau_kernel(const double* __restrict__ T, const double* __restrict__ t1, double c,
+                           double* __restrict__ out, int o, int v) {
+    const long long total = (long long)o * o * v * v;
+    long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; L < total; L += stride) {
+        long long r = L;
+        const int i = (int)(r % o); r /= o;
+        const int j = (int)(r % o); r /= o;
+        const int a = (int)(r % v);
+        const int b = (int)(r / v);
+        const double base = T ? T[L] : 0.0;
+        out[L] = base + c * t1[i + (long long)o * a] * t1[j + (long long)o * b];
+    }
+}
+
+__global__ void divide_Dijab_kernel(const double* __restrict__ R, double* __restrict__ Tn,
+                                    const double* __restrict__ eo, const double* __restrict__ ev, int o,
+                                    int v) {
+    const long long total = (long long)o * o * v * v;
+    long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; L < total; L += stride) {
+        long long r = L;
+        const int i = (int)(r % o); r /= o;
+        const int j = (int)(r % o); r /= o;
+        const int a = (int)(r % v);
+        const int b = (int)(r / v);
+        Tn[L] = R[L] / (eo[i] + eo[j] - ev[a] - ev[b]);
+    }
+}
+
+// Tnew = (V + L1 + L2 + H + P(H)) / D.  One block per (a,b) pair, the o x o slab of H[.,.,b,a] is
+// transposed through shared memory so that every global access is coalesced.
+__global__ void residual_finish_kernel(const double* __restrict__ V, const double* __restrict__ L1,
+                                       const double* __restrict__ L2, const double* __restrict__ H,
+                                       double* __restrict__ Tn, const double* __restrict__ eo,
+                                       const double* __restrict__ ev, int o, int v) {
+    extern __shared__ double sh[];  // o x (o+1)
+    const long long oo = (long long)o * o;
+    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
+        const int a = (int)(ab % v), b = (int)(ab / v);
+        const long long base = ab * oo;
+        const long long baseT = ((long long)a * v + b) * oo;  // slab (b,a): index b + v*a
+        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+            const int i = e % o, j = e / o;
+            sh[i * (o + 1) + j] = H[baseT + e];  // sh[i][j] = H[i,j,b,a]
+        }
+        __syncthreads();
+        const double dab = -ev[a] - ev[b];
+        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+            const int i = e % o, j = e / o;
+            double r = V[base + e] + H[base + e] + sh[j * (o + 1) + i];  // + H[j,i,b,a]
+            if (L1) r += L1[base + e];
+            if (L2) r += L2[base + e];
+            Tn[base + e] = r / (eo[i] + eo[j] + dab);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void divide_Dia_kernel(const double* __restrict__ R, double* __restrict__ tn,
+                                  const double* __restrict__ eo, const double* __restrict__ ev, int o, int v) {
+    const int total = o * v;
+    for (int L = blockIdx.x * blockDim.x + threadIdx.x; L < total; L += gridDim.x * blockDim.x) {
+        const int i = L % o, a = L / o;
+        tn[L] = R[L] / (eo[i] - ev[a]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic reductions
+// ---------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ double block_reduce(double v) {
+    __shared__ double red[THREADS / 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        r = (lane < THREADS / 32) ? red[lane] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) r += __shfl_down_sync(0xffffffffu, r, off);
+    }
+    __syncthreads();
+    return r;  // valid in thread 0
+}
+
+// E = sum V[ijab] (2 X[ijab] - X[jiab]), X = T + t(x)t.  One block per group of (a,b) slabs.
+__global__ void cc_energy_kernel(const double* __restrict__ V, const double* __restrict__ T,
+                                 const double* __restrict__ t1, int o, int v, double* __restrict__ partial) {
+    const long long oo = (long long)o * o;
+    double acc = 0.0;
+    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
+        const int a = (int)(ab % v), b = (int)(ab / v);
+        const long long base = ab * oo;
+        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+            const int i = e % o, j = e / o;
+            double x = T[base + e], xt = T[base + j + (long long)o * i];
+            if (t1) {
+                const double tia = t1[i + (long long)o * a], tjb = t1[j + (long long)o * b];
+                const double tja = t1[j + (long long)o * a], tib = t1[i + (long long)o * b];
+                x += tia * tjb;
+                xt += tja * tib;
+            }
+            acc += V[base + e] * (2.0 * x - xt);
+        }
+    }
+    const double r = block_reduce<256>(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+__global__ void mp2_energy_kernel(const double* __restrict__ V, const double* __restrict__ eo,
+                                  const double* __restrict__ ev, int o, int v, double* __restrict__ partial) {
+    const long long oo = (long long)o * o;
+    double acc = 0.0;
+    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
+        const int a = (int)(ab % v), b = (int)(ab / v);
+        const long long base = ab * oo;
+        const long long baseT = ((long long)b + (long long)v * a) * oo;
+        const double dab = -ev[a] - ev[b];
+        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+            const int i = e % o, j = e / o;
+            const double x = V[base + e];
+            acc += x * (2.0 * x - V[baseT + e]) / (eo[i] + eo[j] + dab);
+        }
+    }
+    const double r = block_reduce<256>(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+__global__ void final_reduce_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+    const double r = block_reduce<256>(acc);
+    if (threadIdx.x == 0) out[0] = r;
+}
+
+__global__ void synth_eri_kernel(double* __restrict__ g, long long n, long long np, long long sig_lo,
+                                 long long sig_count, unsigned long long seed, double scale) {
+    const long long total = np * np * np * sig_count;
+    long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; L < total; L += stride) {
+        long long r = L;
+        const unsigned long long mu = r % np; r /= np;
+        const unsigned long long nu = r % np; r /= np;
+        const unsigned long long lam = r % np;
+        const unsigned long long sig = (unsigned long long)(r / np) + sig_lo;
+        double val = 0.0;
+        if (mu < (unsigned long long)n && nu < (unsigned long long)n && lam < (unsigned long long)n &&
+            sig < (unsigned long long)n) {
+            unsigned long long hi = mu > nu ? mu : nu, lo = mu > nu ? nu : mu;
+            const unsigned long long P = hi * (hi + 1) / 2 + lo;
+            hi = lam > sig ? lam : sig; lo = lam > sig ? sig : lam;
+            const unsigned long long Q = hi * (hi + 1) / 2 + lo;
+            hi = P > Q ? P : Q; lo = P > Q ? Q : P;
+            const unsigned long long K = hi * (hi + 1) / 2 + lo;
+            const unsigned long long h = splitmix64(seed ^ K);
+            const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+            val = scale * (2.0 * u - 1.0);
+        }
+        g[L] = val;
+    }
+}
+
+__global__ void block_copy_kernel(const double* __restrict__ src, double* __restrict__ dst, long long e0,
+                                  long long e1, long long e2, long long e3, long long s1, long long s2,
+                                  long long s3, long long d1, long long d2, long long d3) {
+    const long long total = e0 * e1 * e2 * e3;
+    long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; L < total; L += stride) {
+        long long r = L;
+        const long long i0 = r % e0; r /= e0;
+        const long long i1 = r % e1; r /= e1;
+        const long long i2 = r % e2;
+        const long long i3 = r / e2;
+        dst[i0 + i1 * d1 + i2 * d2 + i3 * d3] = src[i0 + i1 * s1 + i2 * s2 + i3 * s3];
+    }
+}
+
 }  // namespace
 
 int ew_grid(jues_ctx* ctx, size_t n, int threads) {
@@ -31,10 +330,186 @@ int ew_grid(jues_ctx* ctx, size_t n, int threads) {
     return (int)blocks;
 }
 
+#define AUX_LAUNCHED(ctx)           \
+    JUES_CUDA(cudaGetLastError());  \
+    (ctx)->stats.aux_launches++
+
 void fill_pattern(jues_ctx* ctx, double* p, size_t n, unsigned long long seed) {
     fill_pattern_kernel<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(p, n, seed);
-    JUES_CUDA(cudaGetLastError());
-    ctx->stats.aux_launches++;
+    AUX_LAUNCHED(ctx);
+}
+
+void fill(jues_ctx* ctx, double* p, size_t n, double v) {
+    if (!n) return;
+    fill_kernel<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(p, n, v);
+    AUX_LAUNCHED(ctx);
+}
+
+void axpby(jues_ctx* ctx, size_t n, double a, const double* x, double b, double* y) {
+    if (!n) return;
+    axpby_kernel<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(n, a, x, b, y);
+    AUX_LAUNCHED(ctx);
+}
+
+void lincomb2(jues_ctx* ctx, size_t n, double a, const double* x1, double b, const double* x2, double* y) {
+    if (!n) return;
+    lincomb2_kernel<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(n, a, x1, b, x2, y);
+    AUX_LAUNCHED(ctx);
+}
+
+void permute_axpby(jues_ctx* ctx, double alpha, const Ten& in, const char* ii, double beta,
+                   const Ten& out, const char* io) {
+    const int rank = (int)strlen(ii);
+    JUES_REQUIRE(rank == (int)strlen(io) && rank == in.rank && rank == out.rank && rank >= 1 && rank <= 4,
+                 "permute: rank mismatch");
+    long long sin_in[4], s = 1;
+    for (int q = 0; q < rank; ++q) { sin_in[q] = s; s *= in.d[q]; }
+    long long n[4] = {1, 1, 1, 1}, sin[4] = {0, 0, 0, 0}, sout[4] = {0, 0, 0, 0};
+    long long so = 1;
+    for (int q = 0; q < rank; ++q) {
+        const char* f = strchr(ii, io[q]);
+        JUES_REQUIRE(f != nullptr, "permute: index letters differ");
+        const int src = (int)(f - ii);
+        JUES_REQUIRE(in.d[src] == out.d[q], "permute: extent mismatch");
+        n[q] = out.d[q];
+        sin[q] = sin_in[src];
+        sout[q] = so;
+        so *= out.d[q];
+    }
+    const long long total = so;
+    if (total == 0) return;
+    JUES_REQUIRE(in.p != out.p, "permute: in-place not supported");
+    // merge adjacent output axes that are also adjacent (same order) in the input
+    int r = rank;
+    for (int q = 0; q + 1 < r;) {
+        if (sin[q + 1] == sin[q] * n[q]) {
+            n[q] *= n[q + 1];
+            for (int k = q + 1; k + 1 < r; ++k) { n[k] = n[k + 1]; sin[k] = sin[k + 1]; }
+            --r;
+            n[r] = 1; sin[r] = 0;
+        } else {
+            ++q;
+        }
+    }
+    so = 1;
+    for (int q = 0; q < 4; ++q) { sout[q] = so; so *= n[q]; }
+    if (sin[0] == 1) {
+        PermArgs a;
+        for (int q = 0; q < 4; ++q) { a.n[q] = n[q]; a.sin[q] = sin[q]; }
+        a.total = total; a.alpha = alpha; a.beta = beta;
+        permute_same_fast<<<ew_grid(ctx, (size_t)total, 256), 256, 0, ctx->stream>>>(in.p, out.p, a);
+        AUX_LAUNCHED(ctx);
+        return;
+    }
+    int qr = -1;
+    for (int q = 1; q < r; ++q) if (sin[q] == 1) qr = q;
+    JUES_REQUIRE(qr > 0, "permute: internal (no unit-stride axis)");
+    int others[2], no = 0;
+    for (int q = 1; q < 4; ++q) if (q != qr) others[no++] = q;
+    PermT a;
+    a.nc = n[0]; a.nr = n[qr]; a.nu = n[others[0]]; a.nw = n[others[1]];
+    a.sin_c = sin[0]; a.sin_u = sin[others[0]]; a.sin_w = sin[others[1]];
+    a.sout_r = sout[qr]; a.sout_u = sout[others[0]]; a.sout_w = sout[others[1]];
+    a.tiles_c = (a.nc + 31) / 32; a.tiles_r = (a.nr + 31) / 32;
+    a.alpha = alpha; a.beta = beta;
+    const long long blocks = a.tiles_c * a.tiles_r * a.nu * a.nw;
+    JUES_REQUIRE(blocks < (1ll << 31), "permute: grid too large");
+    permute_tiled<<<(unsigned)blocks, dim3(32, 8), 0, ctx->stream>>>(in.p, out.p, a);
+    AUX_LAUNCHED(ctx);
+}
+
+void splitk_reduce(jues_ctx* ctx, const double* W, int nsplit, int64_t M, int64_t N, int64_t batch,
+                   double alpha, double beta, double* C, int64_t ldc, int64_t strideC) {
+    const size_t total = (size_t)M * N * batch;
+    splitk_reduce_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(W, nsplit, M, N, batch, alpha,
+                                                                            beta, C, ldc, strideC);
+    AUX_LAUNCHED(ctx);
+}
+
+void tau_build(jues_ctx* ctx, const double* T, const double* t1, double c, double* out, int64_t o, int64_t v) {
+    const size_t total = (size_t)o * o * v * v;
+    tau_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(T, t1, c, out, (int)o, (int)v);
+    AUX_LAUNCHED(ctx);
+}
+
+void divide_Dijab(jues_ctx* ctx, const double* R, double* Tnew, const double* eo, const double* ev,
+                  int64_t o, int64_t v) {
+    const size_t total = (size_t)o * o * v * v;
+    divide_Dijab_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(R, Tnew, eo, ev, (int)o, (int)v);
+    AUX_LAUNCHED(ctx);
+}
+
+void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const double* L2, const double* H,
+                     double* Tnew, const double* eo, const double* ev, int64_t o, int64_t v) {
+    const size_t smem = (size_t)o * (o + 1) * sizeof(double);
+    JUES_REQUIRE(smem <= 200 * 1024, "residual_finish: nocc too large for the shared-memory slab");
+    static bool attr_done = false;
+    if (!attr_done) {
+        JUES_CUDA(cudaFuncSetAttribute(residual_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
+        attr_done = true;
+    }
+    long long blocks = (long long)v * v;
+    const long long cap = (long long)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    residual_finish_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(V, L1, L2, H, Tnew, eo, ev, (int)o,
+                                                                         (int)v);
+    AUX_LAUNCHED(ctx);
+}
+
+void divide_Dia(jues_ctx* ctx, const double* R1, double* tnew, const double* eo, const double* ev,
+                int64_t o, int64_t v) {
+    divide_Dia_kernel<<<ew_grid(ctx, (size_t)o * v, 256), 256, 0, ctx->stream>>>(R1, tnew, eo, ev, (int)o, (int)v);
+    AUX_LAUNCHED(ctx);
+}
+
+static double finish_reduction(jues_ctx* ctx, int nblocks) {
+    final_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, nblocks, ctx->red_dev + ctx->red_cap - 1);
+    AUX_LAUNCHED(ctx);
+    JUES_CUDA(cudaMemcpyAsync(ctx->red_host, ctx->red_dev + ctx->red_cap - 1, sizeof(double),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ctx->red_host[0];
+}
+
+static int reduction_blocks(jues_ctx* ctx, int64_t v) {
+    long long blocks = (long long)v * v;
+    const long long cap = (long long)ctx->sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks > (long long)ctx->red_cap - 2) blocks = (long long)ctx->red_cap - 2;
+    return (int)blocks;
+}
+
+double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v) {
+    const int blocks = reduction_blocks(ctx, v);
+    cc_energy_kernel<<<blocks, 256, 0, ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
+    AUX_LAUNCHED(ctx);
+    return finish_reduction(ctx, blocks);
+}
+
+double mp2_energy(jues_ctx* ctx, const double* V, const double* eo, const double* ev, int64_t o, int64_t v) {
+    const int blocks = reduction_blocks(ctx, v);
+    mp2_energy_kernel<<<blocks, 256, 0, ctx->stream>>>(V, eo, ev, (int)o, (int)v, ctx->red_dev);
+    AUX_LAUNCHED(ctx);
+    return finish_reduction(ctx, blocks);
+}
+
+void block_copy(jues_ctx* ctx, const double* src, const int64_t sd[4], double* dst, const int64_t dd[4],
+                const int64_t ext[4]) {
+    const size_t total = (size_t)(ext[0] * ext[1] * ext[2] * ext[3]);
+    if (!total) return;
+    block_copy_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(
+        src, dst, ext[0], ext[1], ext[2], ext[3], sd[0], sd[0] * sd[1], sd[0] * sd[1] * sd[2], dd[0],
+        dd[0] * dd[1], dd[0] * dd[1] * dd[2]);
+    AUX_LAUNCHED(ctx);
+}
+
+void synth_eri_fill(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t sig_lo,
+                    int64_t sig_count, unsigned long long seed, double scale) {
+    const size_t total = (size_t)n_padded * n_padded * n_padded * sig_count;
+    synth_eri_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(g, n_logical, n_padded, sig_lo,
+                                                                        sig_count, seed, scale);
+    AUX_LAUNCHED(ctx);
 }
 
 }  // namespace jues

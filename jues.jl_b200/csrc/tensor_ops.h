@@ -1,7 +1,90 @@
-// Element-wise / permutation / reduction kernels.  Internal.
+// Element-wise / permutation / reduction kernels and the dense device tensor view.  Internal.
 #pragma once
 #include "jues_common.h"
 
 namespace jues {
+
+// Dense column-major device tensor view, rank <= 4 (first index fastest).
+struct Ten {
+    double* p = nullptr;
+    int rank = 0;
+    int64_t d[4] = {1, 1, 1, 1};
+    Ten() {}
+    Ten(double* p_, int64_t d0) : p(p_), rank(1) { d[0] = d0; }
+    Ten(double* p_, int64_t d0, int64_t d1) : p(p_), rank(2) { d[0] = d0; d[1] = d1; }
+    Ten(double* p_, int64_t d0, int64_t d1, int64_t d2) : p(p_), rank(3) { d[0] = d0; d[1] = d1; d[2] = d2; }
+    Ten(double* p_, int64_t d0, int64_t d1, int64_t d2, int64_t d3) : p(p_), rank(4) {
+        d[0] = d0; d[1] = d1; d[2] = d2; d[3] = d3;
+    }
+    int64_t size() const { return d[0] * d[1] * d[2] * d[3]; }
+};
+
+// Owning tensor.
+struct DTen {
+    DBuf buf;
+    Ten t;
+    DTen() {}
+    DTen(jues_ctx* ctx, int64_t d0, int64_t d1 = -1, int64_t d2 = -1, int64_t d3 = -1) { alloc(ctx, d0, d1, d2, d3); }
+    void alloc(jues_ctx* ctx, int64_t d0, int64_t d1 = -1, int64_t d2 = -1, int64_t d3 = -1) {
+        int64_t n = d0 * (d1 > 0 ? d1 : 1) * (d2 > 0 ? d2 : 1) * (d3 > 0 ? d3 : 1);
+        buf.alloc(ctx, (size_t)n);
+        t = Ten();
+        t.p = buf.p;
+        t.rank = d3 > 0 ? 4 : d2 > 0 ? 3 : d1 > 0 ? 2 : 1;
+        t.d[0] = d0;
+        if (d1 > 0) t.d[1] = d1;
+        if (d2 > 0) t.d[2] = d2;
+        if (d3 > 0) t.d[3] = d3;
+    }
+    operator Ten() const { return t; }
+    double* p() const { return buf.p; }
+    void release() { buf.release(); t = Ten(); }
+};
+
 int ew_grid(jues_ctx* ctx, size_t n, int threads);
+
+// out[<io order>] = alpha * in[<ii order>] + beta * out   (io is a permutation of ii's letters)
+void permute_axpby(jues_ctx* ctx, double alpha, const Ten& in, const char* ii, double beta,
+                   const Ten& out, const char* io);
+
+// y = a*x + b*y  (same layout, n elements)
+void axpby(jues_ctx* ctx, size_t n, double a, const double* x, double b, double* y);
+// y = a*x1 + b*x2
+void lincomb2(jues_ctx* ctx, size_t n, double a, const double* x1, double b, const double* x2, double* y);
+void fill(jues_ctx* ctx, double* p, size_t n, double v);
+
+// split-K epilogue: C[m,n] = alpha * sum_z W[z][m,n] + beta * C[m,n]   (W slices dense M x N)
+void splitk_reduce(jues_ctx* ctx, const double* W, int nsplit, int64_t M, int64_t N, int64_t batch,
+                   double alpha, double beta, double* C, int64_t ldc, int64_t strideC);
+
+// out[i,j,a,b] = T[i,j,a,b] + c * t[i,a] * t[j,b]        (o,o,v,v), t is (o,v); T may be null (=0)
+void tau_build(jues_ctx* ctx, const double* T, const double* t1, double c, double* out, int64_t o, int64_t v);
+
+// Tnew[i,j,a,b] = R[i,j,a,b] / (eo[i] + eo[j] - ev[a] - ev[b])       (may be in place)
+void divide_Dijab(jues_ctx* ctx, const double* R, double* Tnew, const double* eo, const double* ev,
+                  int64_t o, int64_t v);
+// R = (R0 + L1 + L2 + H + P(H)) / D with P(H)[i,j,a,b] = H[j,i,b,a]; L1, L2 nullable
+void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const double* L2, const double* H,
+                     double* Tnew, const double* eo, const double* ev, int64_t o, int64_t v);
+// tnew[i,a] = R1[i,a] / (eo[i] - ev[a])
+void divide_Dia(jues_ctx* ctx, const double* R1, double* tnew, const double* eo, const double* ev,
+                int64_t o, int64_t v);
+
+// deterministic reductions (fixed-shape two-pass tree); result returned on the host
+// E = sum_{ijab} V[ijab] * (2*X[ijab] - X[jiab]),  X = T + t(x)t (t nullable)
+double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v);
+// E = sum_{ijab} v[ijab] (2 v[ijab] - v[ijba]) / (eo[i]+eo[j]-ev[a]-ev[b])
+double mp2_energy(jues_ctx* ctx, const double* v, const double* eo, const double* ev, int64_t o, int64_t vv);
+
+// counter-based synthetic ERIs (same function as jues.jl_b200.synth.counter_eri_element)
+void synth_eri_fill(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t sig_lo,
+                    int64_t sig_count, unsigned long long seed, double scale);
+
+}  // namespace jues
+
+namespace jues {
+// dst[i0,i1,i2,i3] = src[i0,i1,i2,i3] for i_q < ext[q]; both dense column-major with their own
+// extents (sd, dd >= ext): pads / unpads / slices a rank-4 block on the device.
+void block_copy(jues_ctx* ctx, const double* src, const int64_t sd[4], double* dst, const int64_t dd[4],
+                const int64_t ext[4]);
 }  // namespace jues

@@ -1,0 +1,168 @@
+// 4-index AO->MO transformation (Transformation.jl:39-93, IntegralTransformation.jl:94) as four
+// quarter transforms, each ONE (batched) launch of the sm_100a DGEMM with no permutation pass:
+//   axis 0      : out[d, rest]        = C^T (d x N) * in (N x rest)                 'T','N'
+//   axis 1,2    : out[pre, d, post_b] = in[pre, N, post_b] * C (N x d), batch = post 'N','N'
+//   axis 3      : out[pre, d]         = in[pre, N] * C (N x d)                       'N','N'
+// The contraction order is chosen to minimise flops (the reference always contracts sigma, lambda,
+// nu, mu -- Transformation.jl:68-91 -- which costs 2 N^4 d4 for the first quarter whatever d4 is).
+#include "transform.h"
+#include "dgemm.h"
+
+#include <algorithm>
+
+namespace jues {
+
+const double* SynthGao::slab(jues_ctx* ctx, int64_t lo, int64_t cnt) {
+    const int64_t plane = np * np * np;
+    if ((int64_t)stage.n < plane * cnt) stage.alloc(ctx, (size_t)(plane * cnt));
+    synth_eri_fill(ctx, stage.p, n, np, lo, cnt, seed, scale);
+    return stage.p;
+}
+
+void upload_padded_matrix(jues_ctx* ctx, DBuf& dst, const double* host, int64_t n, int64_t d, int64_t np,
+                          int64_t dp) {
+    dst.alloc(ctx, (size_t)(np * dp));
+    if (np != n || dp != d) dst.zero();
+    if (n > 0 && d > 0)
+        JUES_CUDA(cudaMemcpy2DAsync(dst.p, np * 8, host, n * 8, n * 8, d, cudaMemcpyHostToDevice, ctx->stream));
+}
+
+// copy sigma-planes [lo, lo+cnt) of a host n^4 tensor into a padded (np^3 x cnt) device block
+static void upload_gao_planes(jues_ctx* ctx, double* dst, const double* host, int64_t n, int64_t np,
+                              int64_t lo, int64_t cnt) {
+    const int64_t plane = np * np * np;
+    if (n == np) {
+        JUES_CUDA(cudaMemcpyAsync(dst, host + lo * n * n * n, (size_t)(plane * cnt) * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        return;
+    }
+    JUES_CUDA(cudaMemsetAsync(dst, 0, (size_t)(plane * cnt) * sizeof(double), ctx->stream));
+    for (int64_t s = 0; s < cnt && lo + s < n; ++s) {
+        cudaMemcpy3DParms p = {};
+        p.srcPtr = make_cudaPitchedPtr((void*)(host + (lo + s) * n * n * n), n * 8, n, n);
+        p.dstPtr = make_cudaPitchedPtr((void*)(dst + s * plane), np * 8, np, np);
+        p.extent = make_cudaExtent(n * 8, n, n);
+        p.kind = cudaMemcpyHostToDevice;
+        JUES_CUDA(cudaMemcpy3DAsync(&p, ctx->stream));
+    }
+}
+
+const double* HostGao::slab(jues_ctx* ctx, int64_t lo, int64_t cnt) {
+    const int64_t plane = np * np * np;
+    if ((int64_t)stage.n < plane * cnt) stage.alloc(ctx, (size_t)(plane * cnt));
+    upload_gao_planes(ctx, stage.p, h, n, np, lo, cnt);
+    return stage.p;
+}
+
+void upload_padded_gao(jues_ctx* ctx, double* dst, const double* host, int64_t n, int64_t np) {
+    if (!dst) return;
+    upload_gao_planes(ctx, dst, host, n, np, 0, np);
+}
+
+namespace {
+
+double quarter_flops(const int64_t e[4], int axis, int64_t d) {
+    return 2.0 * (double)e[0] * (double)e[1] * (double)e[2] * (double)e[3] * (double)d;
+}
+
+// choose the contraction order (a permutation of axes 0..3) with the fewest flops
+void best_order(int64_t np, const int64_t dp[4], bool ref_order, bool streamed, int order[4], double* flops) {
+    int perm[4] = {0, 1, 2, 3};
+    double best = 1e300;
+    int best_perm[4] = {3, 2, 1, 0};
+    if (ref_order) {
+        int64_t e[4] = {np, np, np, np};
+        double f = 0;
+        for (int s = 0; s < 4; ++s) { f += quarter_flops(e, best_perm[s], dp[best_perm[s]]); e[best_perm[s]] = dp[best_perm[s]]; }
+        best = f;
+    } else {
+        do {
+            if (streamed && perm[0] != 3) continue;
+            int64_t e[4] = {np, np, np, np};
+            double f = 0;
+            for (int s = 0; s < 4; ++s) { f += quarter_flops(e, perm[s], dp[perm[s]]); e[perm[s]] = dp[perm[s]]; }
+            // tie-break towards the reference order (last axis first)
+            if (f < best * (1.0 - 1e-12)) { best = f; std::copy(perm, perm + 4, best_perm); }
+        } while (std::next_permutation(perm, perm + 4));
+    }
+    std::copy(best_perm, best_perm + 4, order);
+    if (flops) *flops = best;
+}
+
+// one quarter transform of a dense device tensor `in` with extents e[4] along `axis`
+void quarter(jues_ctx* ctx, const double* in, const int64_t e[4], int axis, const double* Cm, int64_t np,
+             int64_t d, double* out, double beta = 0.0, int64_t k_lo = 0, int64_t k_cnt = -1) {
+    int64_t pre = 1, post = 1;
+    for (int q = 0; q < axis; ++q) pre *= e[q];
+    for (int q = axis + 1; q < 4; ++q) post *= e[q];
+    const int64_t nk = k_cnt < 0 ? e[axis] : k_cnt;
+    GemmCall g;
+    g.K = nk;
+    g.beta = beta;
+    if (axis == 0) {
+        g.transA = true; g.transB = false;
+        g.M = d; g.N = post;
+        g.A = Cm + k_lo; g.lda = np;
+        g.B = in; g.ldb = e[0];
+        g.C = out; g.ldc = d;
+    } else {
+        g.transA = false; g.transB = false;
+        g.M = pre; g.N = d;
+        g.A = in; g.lda = pre; g.strideA = pre * e[axis];
+        g.B = Cm + k_lo; g.ldb = np; g.strideB = 0;
+        g.C = out; g.ldc = pre; g.strideC = pre * d;
+        g.batch = post;
+    }
+    dgemm(ctx, g);
+}
+
+}  // namespace
+
+double tei_transform_flops(int64_t np, const int64_t dp[4], bool reference_order, bool streamed) {
+    int order[4];
+    double f;
+    best_order(np, dp, reference_order, streamed, order, &f);
+    return f;
+}
+
+void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4], const int64_t dp[4],
+                       double* out, bool reference_order) {
+    const int64_t np = gao.np;
+    int order[4];
+    best_order(np, dp, reference_order, !gao.resident(), order, nullptr);
+    int64_t e[4] = {np, np, np, np};
+    DBuf cur, nxt;
+    const double* src = gao.base();
+    for (int s = 0; s < 4; ++s) {
+        const int ax = order[s];
+        int64_t e2[4] = {e[0], e[1], e[2], e[3]};
+        e2[ax] = dp[ax];
+        const size_t nout = (size_t)(e2[0] * e2[1] * e2[2] * e2[3]);
+        double* dst;
+        if (s == 3) dst = out;
+        else { nxt.alloc(ctx, nout); dst = nxt.p; }
+        if (s == 0 && !gao.resident()) {
+            // stream sigma slabs:  tmp[mu nu lam, b] += g[mu nu lam, slab] * C4[slab, b]
+            JUES_REQUIRE(ax == 3, "internal: streamed transform must contract the last index first");
+            const int64_t plane = np * np * np;
+            int64_t cnt = std::max<int64_t>(2, std::min<int64_t>(np, (int64_t)(2.0e9 / 8.0 / (double)plane)));
+            if (getenv("JUES_B200_FORCE_STREAM")) cnt = std::min<int64_t>(cnt, 6);  // testing: several slabs
+            cnt &= ~int64_t(1);
+            for (int64_t lo = 0; lo < np; lo += cnt) {
+                const int64_t c = std::min(cnt, np - lo);
+                const double* sl = gao.slab(ctx, lo, c);
+                int64_t es[4] = {np, np, np, c};
+                quarter(ctx, sl, es, 3, Cm[3], np, dp[3], dst, lo == 0 ? 0.0 : 1.0, lo, c);
+            }
+        } else {
+            quarter(ctx, src, e, ax, Cm[ax], np, dp[ax], dst);
+        }
+        if (s < 3) {
+            cur = std::move(nxt);
+            src = cur.p;
+        }
+        e[ax] = dp[ax];
+    }
+}
+
+}  // namespace jues
