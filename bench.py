@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark on B200.
+
+BASELINE.json metric: "RCCSD s/iteration + 4-index transform TFLOP/s (FP64) at 1/2/4/8 B200 vs
+CPU".  One JSON line is printed by rank 0:
+
+  * a "step" is ONE RCCSD sweep (all intermediates, T1 and T2 updates, and the energy the reference
+    evaluates every sweep -- RCCSD.jl:150-173,104) on device-resident integrals and amplitudes;
+    `ms_per_step` is therefore the "RCCSD s/iteration" figure (x1000) and `value` the same thing
+    as whole-job FP64 throughput: floating-point operations the GEMM kernels executed per sweep
+    (never more than the algorithmic count F_alg of SURVEY.md section 8a) / seconds per sweep.
+  * `tei_transform` holds the 4-index transform part of the metric (TFLOP/s of the full
+    tei_transform(gao, C) of the same AO tensor, executed flops = 8 N^5).
+  * `e2e` is the same metric through the reference-facing C-ABI call with HOST buffers (pinned):
+    one complete do_rccsd (H2D of gao/C/eps + integral transformation + 40 sweeps + energy D2H).
+  * `roofline` is the dominant kernel (the TMA+DMMA FP64 GEMM at the particle-particle-ladder
+    shape), timed live with CUDA events on the library's stream, against the measured cuBLAS FP64
+    peak of this pool (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json records no FP64 figure).
+  * `cpu_baseline` is the oracle (numpy restatement of the reference's literal algorithm, "port")
+    timed on this box's host cores on a bounded sample.
+
+`--impl reference` times the reference's CPU algorithm (the oracle port; there is no Julia here)
+on the same config and prints the same line shape.
+
+Workload at N=1: BASELINE config 3 (RCCSD, synthetic ERIs, nbf=120, nocc=20), the largest
+single-GPU configuration in BASELINE.json (the nbf=460 configuration the metric is quoted on
+needs 205 GB for <vv|vv> alone and is the 8-GPU case).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+NBF, NOCC = 120, 20
+SEED = 2024
+REF_MAXIT = 40          # RCCSD.jl:36
+
+
+def flops_alg_rccsd(o, v):
+    """F_alg of SURVEY.md section 8a (factorised RCCSD sweep)."""
+    return 2 * o**2 * v**4 + 22 * o**3 * v**3 + 4 * o**4 * v**2 + 24 * o**2 * v**3 + 24 * o**3 * v**2
+
+
+def flops_ref_rccsd(o, v):
+    """F_ref: the reference's literal sweep (Wabef built and applied, 13 ring-type terms)."""
+    return 4 * o**2 * v**4 + 4 * o * v**4 + 26 * o**3 * v**3 + 4 * o**4 * v**2 + 16 * o**2 * v**3
+
+
+def make_inputs(pinned: bool):
+    import jues.jl_b200 as jb
+    scale = 1.7 * jb.synth.default_scale(NBF)     # uniform deviates: same variance as N(0, (0.4/N)^2)
+    Cao, Cav, eps = jb.synth.orbitals(NBF, NOCC, SEED)
+    g = jb.synth.counter_eri(NBF, SEED, scale)
+    if pinned:
+        import torch
+        t = torch.empty(g.size, dtype=torch.float64).pin_memory()
+        gp = t.numpy().reshape(g.shape, order="F")
+        gp[...] = g
+        return gp, Cao, Cav, eps, scale, t
+    return g, Cao, Cav, eps, scale, None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fp64_peak():
+    """Measured cuBLAS FP64 GEMM peak of this pool's B200 (tools/cublas_peak.py)."""
+    p = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+    try:
+        d = json.load(open(p))
+        return float(d["fp64_tflops"]), "profiles/fp64_peak_r01.json (cuBLAS DGEMM burst, measured on this pool)"
+    except Exception:
+        return 37.0, "fallback: DMMA issue-rate ceiling 148 SM x 64 FMA/clk x 1.965 GHz"
+
+
+def traffic_from_profile():
+    p = os.path.join(ROOT, "profiles", "ncu_dgemm_ladder_r01.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on host cores
+# ------------------------------------------------------------------------------------------
+_ORACLE_STATE = {}
+
+
+def run_oracle_sample(n_iter: int):
+    """15 literal transforms (RCCSD.jl:117-142; done once per process and timed) + n_iter literal
+    sweeps at the bench config.  Returns (t_transform, t_iter_avg, energy_after_first_sweep)."""
+    from oracle import jues_oracle as orc
+    o, v = NOCC, NBF - NOCC
+    st = _ORACLE_STATE
+    if not st:
+        g, Cao, Cav, eps, scale, _ = make_inputs(False)
+        t0 = time.perf_counter()
+        st["I"] = orc.make_rccsd_integrals(g, Cao, Cav)
+        st["t_tr"] = time.perf_counter() - t0
+        st["Dia"], st["D"] = orc.form_Dia(o, v, eps), orc.form_Dijab(o, v, eps)
+        del g
+    I, Dia, D = st["I"], st["Dia"], st["D"]
+    T1, T2 = np.zeros((o, v)), I["oovv"] / D
+    e1 = None
+    t0 = time.perf_counter()
+    for k in range(n_iter):
+        T1, T2 = orc.rccsd_iteration(I, T1, T2, Dia, D)
+        e = orc.rccsd_energy(I["oovv"], T1, T2)
+        if k == 0:
+            e1 = e
+    t_it = (time.perf_counter() - t0) / max(n_iter, 1)
+    return st["t_tr"], t_it, e1
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    o, v = NOCC, NBF - NOCC
+    cores = os.cpu_count() or 1
+    t_tr_s, t_it_s = [], []
+    n_iter = 1
+    for step in range(args.warmup + args.steps):
+        t_tr, t_it, e = run_oracle_sample(n_iter)
+        if step >= args.warmup:
+            t_tr_s.append(t_tr); t_it_s.append(t_it)
+    t_tr, t_it = float(np.mean(t_tr_s)), float(np.mean(t_it_s))
+    F = flops_alg_rccsd(o, v)
+    t_call = t_tr + REF_MAXIT * t_it            # a complete do_rccsd: transforms + 40 sweeps
+    tf = F / t_it * 1e-12
+    e2e_tf = REF_MAXIT * F / t_call * 1e-12     # same numerator as the GPU arm: 40 sweeps of F_alg
+    line = {
+        "impl": "reference", "metric": "rccsd_iteration_fp64_tflops", "value": tf, "unit": "TFLOP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_it * 1e3,
+        "s_per_iteration": t_it, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"RCCSD nbf={NBF} nocc={NOCC} nvir={v} (BASELINE config 3), synthetic counter-based ERIs",
+                   "algorithm": "reference literal: 15 tei_transforms + sweeps with materialised Wabef (numpy/OpenBLAS port)"},
+        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                         "sample": f"15 literal transforms ({t_tr:.2f} s) + {n_iter} literal sweep(s) ({t_it:.2f} s each) "
+                                   f"per step; do_rccsd extrapolated to {REF_MAXIT} sweeps"},
+        "e2e": {"value": e2e_tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "s_per_do_rccsd": t_call, "s_per_iteration": t_call / REF_MAXIT},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def gpu_arm(args, rank, world):
+    import torch
+    import jues.jl_b200 as jb
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+    o, v = NOCC, NBF - NOCC
+    ctx = jb.Context(local)
+    g, Cao, Cav, eps, scale, keep = make_inputs(True)
+    gdev = jb.DeviceFourTensor.synth_eri(NBF, seed=SEED, scale=scale, ctx=ctx)   # inputs resident in HBM
+    wdev = jb.Wfn(NOCC, v, eps, Cao, Cav, gdev)
+    whost = jb.Wfn(NOCC, v, eps, Cao, Cav, g)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- value: K timed sweeps after W warm-up sweeps, device-resident inputs --------------
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    hist = []
+    e = jb.RCCSD.do_rccsd(wdev, ctx=ctx, _maxit=args.warmup + args.steps, _e_hist=hist)
+    barrier()
+    ph = ctx.phases()
+    cnt = ctx.counters()
+    it_ms = [ms for k, ms in ph if k == "cc.iteration"]
+    timed = it_ms[args.warmup:]
+    assert len(timed) == args.steps
+    ms_step = float(np.sum(timed)) / args.steps
+    tr_ms = [ms for k, ms in ph if k == "cc.transform"][0]
+    # executed GEMM flops per sweep: subtract the transform's share by running the counters on
+    # a zero-sweep call
+    jb.RCCSD.do_rccsd(wdev, ctx=ctx, _maxit=0)
+    c0 = ctx.counters()
+    flops_step = (cnt["gemm_flops"] - c0["gemm_flops"]) / (args.warmup + args.steps)
+    launches_step = ((cnt["gemm_launches"] - c0["gemm_launches"]) + (cnt["aux_launches"] - c0["aux_launches"])) \
+        / (args.warmup + args.steps)
+
+    # ---- the 4-index transform part of the metric: full tei_transform(gao, C), resident ----
+    Cfull = np.asfortranarray(np.hstack([Cao, Cav]))
+    for _ in range(2):
+        out = jb.tei_transform(gdev, Cfull, "bench", ctx=ctx)
+        out.free()
+    tt_ms = [ms for k, ms in ctx.phases() if k == "tei.transform"][0]
+    tei = {"workload": f"tei_transform(gao, C) nbf={NBF} (all four indices, 8 N^5 flop)", "ms": tt_ms,
+           "tflops": ctx.counters()["gemm_flops"] / tt_ms * 1e-9}
+
+    # ---- e2e: one complete do_rccsd through the C ABI from pinned HOST buffers ----------------
+    e2e_t = []
+    for rep in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        e_host = jb.RCCSD.do_rccsd(whost, ctx=ctx)          # 40 sweeps, the reference's count
+        torch.cuda.synchronize()
+        e2e_t.append(time.perf_counter() - t0)
+    t_call = min(e2e_t)
+    c_full = ctx.counters()
+    clocks = sampler.stop()
+
+    # ---- roofline of the dominant kernel, timed live (CUDA events on the library's stream) ----
+    M, Nn, K = o * o, v * v, v * v                       # particle-particle ladder tau(ij,ef) x <ab|ef>
+    ms_gemm = ctx.gemm_bench("N", "N", M, Nn, K, reps=5)
+    peak, peak_src = fp64_peak()
+    ach = 2.0 * M * Nn * K / ms_gemm * 1e-9
+    roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic_from_profile(),
+                "kernel": "jues::gemm::dgemm_tma_dmma (FP64 DMMA.8x8x4 fed by TMA)",
+                "shape": f"pp-ladder GEMM M={M} N={Nn} K={K}", "ms_per_launch": ms_gemm, "peak_source": peak_src,
+                "sweep_frac_of_peak": flops_step / (ms_step * 1e-3) * 1e-12 / peak}
+
+    # ---- max over ranks -----------------------------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([ms_step, t_call], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, t_call = float(t[0]), float(t[1])
+
+    if rank != 0:
+        return
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only), bounded sample ------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        t_tr, t_it, e_cpu = run_oracle_sample(1)
+        cpu = {"value": flops_alg_rccsd(o, v) / t_it * 1e-12, "unit": "TFLOP/s", "cores": os.cpu_count() or 1,
+               "kind": "port", "s_per_iteration": t_it, "s_transforms": t_tr,
+               "sample": f"oracle (numpy/OpenBLAS port of the reference's literal algorithm): 15 transforms "
+                         f"({t_tr:.1f} s) + 1 sweep ({t_it:.1f} s) at nbf={NBF} nocc={NOCC}",
+               "energy_check": abs(e_cpu - hist[1]) if len(hist) > 1 else None}
+    F_alg = flops_alg_rccsd(o, v)
+    line = {
+        # algorithmic FP64 throughput: F_alg per sweep / seconds per sweep (both arms use F_alg);
+        # the flops the kernels actually executed (<= F_alg) are in config and roofline
+        "metric": "rccsd_iteration_fp64_tflops", "value": F_alg / (ms_step * 1e-3) * 1e-12,
+        "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "s_per_iteration": ms_step * 1e-3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"RCCSD nbf={NBF} nocc={NOCC} nvir={v} (BASELINE config 3), synthetic counter-based ERIs seed={SEED}",
+                   "step": "one RCCSD sweep (intermediates + T1 + T2 + energy) on device-resident data",
+                   "l2": "inputs larger than L2 (<vv|vv> 0.8 GB, amplitudes/intermediates 32 MB each, re-streamed every sweep)",
+                   "flops_executed_per_sweep": flops_step, "F_alg_per_sweep": F_alg, "F_ref_per_sweep": flops_ref_rccsd(o, v)},
+        "tei_transform": tei,
+        "e2e": {"value": REF_MAXIT * F_alg / t_call * 1e-12, "unit": "TFLOP/s",
+                "flops_executed": c_full["gemm_flops"],
+                "h2d_bytes_per_step": int(g.nbytes + Cao.nbytes + Cav.nbytes + eps.nbytes),
+                "d2h_bytes_per_step": int(8 * (REF_MAXIT + 2)),
+                "s_per_do_rccsd": t_call, "s_per_iteration": t_call / REF_MAXIT,
+                "what": "jues_b200_rccsd(host gao, Cao, Cav, eps, maxit=40): H2D + transform + 40 sweeps + energies D2H"},
+        "gpu_launches": int(round(launches_step)),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "energy": {"E_ccsd_after_timed_sweeps": e, "E_ccsd_40_sweeps_e2e": e_host},
+        "integral_transform_ms": tr_ms,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    gpu_arm(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

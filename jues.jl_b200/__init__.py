@@ -224,11 +224,16 @@ def _ranger(idx, dim):
         i = int(idx)
         if i < 0:
             i += dim
+        if not 0 <= i < dim:
+            raise JuesError(-1, f"index {idx} out of range for extent {dim}")
         return i, i + 1, True
     if isinstance(idx, slice):
-        lo, hi, step = idx.indices(dim)
-        if step != 1:
+        if idx.step not in (None, 1):
             raise JuesError(-1, "DeviceFourTensor slices must have unit stride")
+        for b in (idx.start, idx.stop):           # Julia raises BoundsError; do not clamp silently
+            if b is not None and not (-dim <= b <= dim):
+                raise JuesError(-1, f"slice {idx} out of range for extent {dim}")
+        lo, hi, _ = idx.indices(dim)
         return lo, max(hi, lo), False
     raise JuesError(-1, f"unsupported index {idx!r}")
 

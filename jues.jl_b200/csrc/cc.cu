@@ -276,10 +276,12 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
     report(0, res.e_hist[0]);
     for (int it = 1; it <= maxit; ++it) {
         {
+            // one timed "step" = one sweep + the energy the reference evaluates every sweep
+            // (RCCSD.jl:104); the energy read-back is the step's device->host result
             Timer t(ctx, "cc.iteration");
             cc.iterate();
+            res.e_hist[it] = cc.energy();
         }
-        res.e_hist[it] = cc.energy();   // RCCSD.jl:104 evaluates the energy every sweep
         report(it, res.e_hist[it]);
     }
     res.energy = res.e_hist[maxit];
