@@ -58,7 +58,7 @@ def flops_ref_rccsd(o, v):
 
 def make_inputs(pinned: bool):
     import jues.jl_b200 as jb
-    scale = 1.7 * jb.synth.default_scale(NBF)     # uniform deviates: same variance as N(0, (0.4/N)^2)
+    scale = jb.synth.counter_scale(NBF)           # same element variance as the dense generator; converges
     Cao, Cav, eps = jb.synth.orbitals(NBF, NOCC, SEED)
     g = jb.synth.counter_eri(NBF, SEED, scale)
     if pinned:

@@ -267,7 +267,7 @@ class DeviceFourTensor:
                   ctx: Optional[Context] = None) -> "DeviceFourTensor":
         """Counter-based synthetic ERIs generated on the device (== synth.counter_eri)."""
         t = cls(nbf, nbf, nbf, nbf, ctx=ctx)
-        s = synth.default_scale(nbf) if scale is None else scale
+        s = synth.counter_scale(nbf) if scale is None else scale
         t.ctx._check(t.ctx._lib.jues_b200_t4_synth_eri(t._h, C.c_uint64(seed), s))
         return t
 

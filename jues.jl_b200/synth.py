@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["dense_eri", "orbitals", "dense_inputs", "counter_eri", "counter_eri_element",
+__all__ = ["dense_eri", "orbitals", "dense_inputs", "counter_eri", "counter_eri_element", "counter_scale",
            "default_scale"]
 
 _MASK = (1 << 64) - 1
@@ -28,6 +28,13 @@ def default_scale(nbf: int) -> float:
     """s = 0.4/N keeps the un-accelerated Jacobi CC iterations of the reference convergent
     (SURVEY.md section 8d)."""
     return 0.4 / nbf
+
+
+def counter_scale(nbf: int) -> float:
+    """Scale for the counter-based (uniform, un-averaged) generator that gives its elements the
+    same standard deviation as `dense_eri` (normal deviates averaged over the 8 permutations):
+    0.4/N * sqrt(3/8).  Larger values make the reference's DIIS-free Jacobi sweeps diverge."""
+    return default_scale(nbf) * (3.0 / 8.0) ** 0.5
 
 
 def dense_eri(nbf: int, seed: int = 2024, scale: float | None = None) -> np.ndarray:
@@ -97,7 +104,7 @@ def counter_eri(nbf: int, seed: int = 2024, scale: float | None = None,
                 sig_range: tuple[int, int] | None = None) -> np.ndarray:
     """Dense (Fortran-order) array of the counter-based ERIs, optionally only the slab
     sig in [lo, hi) (shape (nbf, nbf, nbf, hi-lo))."""
-    s = default_scale(nbf) if scale is None else scale
+    s = counter_scale(nbf) if scale is None else scale
     lo, hi = (0, nbf) if sig_range is None else sig_range
     idx = np.arange(nbf, dtype=np.uint64)
     sig = np.arange(lo, hi, dtype=np.uint64)
