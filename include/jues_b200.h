@@ -124,6 +124,10 @@ int jues_b200_t4_get_slice(const jues_t4* t, const int64_t lo[4], const int64_t 
 /* Fill with the counter-based synthetic 8-fold-symmetric ERIs of SURVEY.md section 8d
  * (bit-identical to jues.jl_b200.synth.counter_eri on the host).                             */
 int jues_b200_t4_synth_eri(jues_t4* t, uint64_t seed, double scale);
+/* The same synthetic tensor WITHOUT storage: a read-only (nao,nao,nao,nao) handle whose sigma slabs
+ * are generated on demand while a transformation streams through them -- for shapes whose dense
+ * N^4 does not fit in HBM (BASELINE configs 4 and 5: 358-500 GB).                              */
+int jues_b200_t4_create_synth(jues_ctx* ctx, int64_t nao, uint64_t seed, double scale, jues_t4** out);
 
 /* Entry points taking a device-resident gao (Wfn.ao_eri::DiskFourTensor dispatch,
  * Wavefunction.jl:87; Transformation.jl:94-192).  Inputs are already in HBM when they start. */
@@ -154,6 +158,8 @@ typedef struct {
 int jues_b200_get_phases(jues_ctx* ctx, jues_b200_phase* out, int cap);
 int jues_b200_get_counters(jues_ctx* ctx, double* gemm_flops, int64_t* gemm_launches,
                            int64_t* aux_launches, int64_t* bytes_peak);
+/* NCCL collectives issued by the last call and the bytes this rank received in them.           */
+int jues_b200_get_comm_counters(jues_ctx* ctx, int64_t* collectives, double* bytes_received);
 /* Time `reps` back-to-back launches of the DGEMM kernel on device-resident random operands
  * (no host traffic); returns average ms per launch.  Used for the roofline line.            */
 int jues_b200_dgemm_bench(jues_ctx* ctx, char transA, char transB, int64_t M, int64_t N, int64_t K,

@@ -151,6 +151,34 @@ class Context:
         return {"gemm_flops": fl.value, "gemm_launches": gl.value, "aux_launches": al.value,
                 "bytes_peak": bp.value}
 
+    def comm_counters(self):
+        n, b = C.c_int64(), C.c_double()
+        self._check(self._lib.jues_b200_get_comm_counters(self._h, C.byref(n), C.byref(b)))
+        return {"collectives": n.value, "bytes_received": b.value}
+
+    # -- multi-GPU: one process per GPU ---------------------------------------------------------
+    def init_dist(self, rank: Optional[int] = None, nranks: Optional[int] = None):
+        """Attach this context to the job's NCCL communicator.  The 128-byte unique id is made by
+        rank 0 (jues_b200_nccl_unique_id) and broadcast with torch.distributed, which the host
+        program must have initialised (any backend; gloo is enough)."""
+        import torch
+        import torch.distributed as dist
+        rank = dist.get_rank() if rank is None else rank
+        nranks = dist.get_world_size() if nranks is None else nranks
+        idbuf = (C.c_ubyte * 128)()
+        if nranks > 1:
+            if rank == 0:
+                rc = self._lib.jues_b200_nccl_unique_id(idbuf)
+                if rc != 0:
+                    raise JuesError(rc, self._lib.jues_b200_last_error(None).decode())
+            t = torch.tensor(list(bytes(idbuf)), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, src=0)
+            idbuf = (C.c_ubyte * 128)(*t.cpu().tolist())
+        self._check(self._lib.jues_b200_init_dist(self._h, int(rank), int(nranks), idbuf))
+        self.rank, self.nranks = rank, nranks
+
     def set_amplitude_callback(self, fn):
         """fn(it, energy, T1 or None, T2) after the guess and after every sweep (tests)."""
         if fn is None:
@@ -200,6 +228,15 @@ class Context:
         self._check(self._lib.jues_b200_dgemm_bench(self._h, tA.encode(), tB.encode(), M, N, K, reps,
                                                     C.byref(ms)))
         return ms.value
+
+
+def slab_bounds(nvir: int, nranks: int, rank: int):
+    """Host-side mirror of the library's partition of the virtual index over ranks
+    (csrc/cc.cu: setup_problem + dist.h: slab_of): nvir is padded to a multiple of 2*nranks and
+    split into equal slabs.  Returns (padded nvir, first, last+1) of `rank`'s slab."""
+    vp = -(-int(nvir) // (2 * nranks)) * (2 * nranks)
+    vs = vp // nranks
+    return vp, rank * vs, (rank + 1) * vs
 
 
 _default_ctx: Optional[Context] = None
@@ -264,8 +301,16 @@ class DeviceFourTensor:
 
     @classmethod
     def synth_eri(cls, nbf: int, seed: int = 2024, scale: Optional[float] = None,
-                  ctx: Optional[Context] = None) -> "DeviceFourTensor":
-        """Counter-based synthetic ERIs generated on the device (== synth.counter_eri)."""
+                  ctx: Optional[Context] = None, virtual: bool = False) -> "DeviceFourTensor":
+        """Counter-based synthetic ERIs generated on the device (== synth.counter_eri).
+        virtual=True: no storage; sigma slabs are generated on demand while a transformation
+        streams through them (for nbf whose dense N^4 does not fit in HBM); read-only."""
+        if virtual:
+            ctx = ctx or default_context()
+            s = synth.counter_scale(nbf) if scale is None else scale
+            h = C.c_void_p()
+            ctx._check(ctx._lib.jues_b200_t4_create_synth(ctx._h, nbf, C.c_uint64(seed), s, C.byref(h)))
+            return cls(nbf, nbf, nbf, nbf, ctx=ctx, _handle=h)
         t = cls(nbf, nbf, nbf, nbf, ctx=ctx)
         s = synth.counter_scale(nbf) if scale is None else scale
         t.ctx._check(t.ctx._lib.jues_b200_t4_synth_eri(t._h, C.c_uint64(seed), s))

@@ -52,6 +52,9 @@ SIGNATURES = {
     "jues_b200_t4_set_slice": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_double_p]),
     "jues_b200_t4_get_slice": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_double_p]),
     "jues_b200_t4_synth_eri": (C.c_int, [C.c_void_p, C.c_uint64, C.c_double]),
+    "jues_b200_t4_create_synth": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_double,
+                                            C.POINTER(C.c_void_p)]),
+    "jues_b200_get_comm_counters": (C.c_int, [C.c_void_p, c_int64_p, c_double_p]),
     "jues_b200_tei_transform_t4": (C.c_int, [C.c_void_p, C.c_void_p,
                                              c_double_p, C.c_int64, c_double_p, C.c_int64,
                                              c_double_p, C.c_int64, c_double_p, C.c_int64,

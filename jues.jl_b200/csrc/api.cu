@@ -33,7 +33,9 @@ void make_host_gao(jues_ctx* ctx, HostGaoHolder& h, const double* gao, int64_t n
     const double bytes = (double)np * np * np * np * 8.0;
     const double avail = (double)free_device_bytes() + 0.0;
     const bool force_stream = getenv("JUES_B200_FORCE_STREAM") != nullptr;  // testing hook
-    if (need_resident || (!force_stream && bytes < 0.45 * avail)) {
+    // coupled cluster keeps a second, re-ordered copy next to the AO tensor: budget twice the bytes
+    const double need = need_resident ? 2.0 * bytes : bytes;
+    if (!force_stream && need < 0.45 * avail) {
         Timer t(ctx, "h2d.gao");
         h.dense.alloc(ctx, (size_t)(np * np * np * np));
         upload_padded_gao(ctx, h.dense.p, gao, nao, np);
@@ -44,10 +46,19 @@ void make_host_gao(jues_ctx* ctx, HostGaoHolder& h, const double* gao, int64_t n
 }
 
 void check_t4_is_gao(const jues_t4* g) {
-    JUES_REQUIRE(g && g->p, "null tensor handle");
+    JUES_REQUIRE(g && (g->p || g->virtual_synth), "null tensor handle");
     JUES_REQUIRE(g->d[0] == g->d[1] && g->d[1] == g->d[2] && g->d[2] == g->d[3],
                  "gao handle must be (nao,nao,nao,nao)");
 }
+
+// GaoSource of a tensor handle: dense storage or on-demand synthetic slabs
+struct T4Source {
+    std::unique_ptr<GaoSource> src;
+    explicit T4Source(const jues_t4* g) {
+        if (g->virtual_synth) src.reset(new SynthGao(g->d[0], g->dp[0], g->seed, g->scale));
+        else src.reset(new DeviceGao(g->p, g->d[0], g->dp[0]));
+    }
+};
 
 // download a padded device tensor (dp) into an unpadded host array (d)
 void download_block(jues_ctx* ctx, const double* dev, const int64_t dp[4], double* host, const int64_t d[4]) {
@@ -133,7 +144,8 @@ extern "C" int jues_b200_tei_transform_t4(jues_ctx* ctx, const jues_t4* gao, con
     check_t4_is_gao(gao);
     JUES_REQUIRE(out != nullptr, "null output");
     Timer total(ctx, "total");
-    DeviceGao src(gao->p, gao->d[0], gao->dp[0]);
+    T4Source holder(gao);
+    GaoSource& src = *holder.src;
     const double* Ch[4] = {C1, C2, C3, C4};
     const int64_t d[4] = {d1, d2, d3, d4};
     DBuf res;
@@ -176,7 +188,8 @@ extern "C" int jues_b200_rmp2_t4(jues_ctx* ctx, const jues_t4* gao, const double
     Timer total(ctx, "total");
     Problem P;
     setup_problem(ctx, P, gao->d[0], Cao, nocc, Cav, nvir, eps);
-    DeviceGao src(gao->p, gao->d[0], gao->dp[0]);
+    T4Source holder(gao);
+    GaoSource& src = *holder.src;
     *e_mp2 = rmp2_dev(ctx, P, src);
     JUES_API_END(ctx)
 }
@@ -219,7 +232,8 @@ extern "C" int jues_b200_rccd_t4(jues_ctx* ctx, const jues_t4* gao, const double
     check_t4_is_gao(gao);
     JUES_REQUIRE(guess_mode == 0 || guess_mode == 1, "guess_mode must be 0 (reference) or 1 (MP2)");
     Timer total(ctx, "total");
-    DeviceGao src(gao->p, gao->d[0], gao->dp[0]);
+    T4Source holder(gao);
+    GaoSource& src = *holder.src;
     run_cc(ctx, src, Cao, nocc, Cav, nvir, eps, false, maxit, guess_mode, e_ccd, e_hist, nullptr, T2_out);
     JUES_API_END(ctx)
 }
@@ -243,7 +257,8 @@ extern "C" int jues_b200_rccsd_t4(jues_ctx* ctx, const jues_t4* gao, const doubl
     begin_call(ctx);
     check_t4_is_gao(gao);
     Timer total(ctx, "total");
-    DeviceGao src(gao->p, gao->d[0], gao->dp[0]);
+    T4Source holder(gao);
+    GaoSource& src = *holder.src;
     run_cc(ctx, src, Cao, nocc, Cav, nvir, eps, true, maxit, 1, e_ccsd, e_hist, T1_out, T2_out);
     JUES_API_END(ctx)
 }
@@ -272,6 +287,26 @@ extern "C" int jues_b200_t4_create(jues_ctx* ctx, int64_t d1, int64_t d2, int64_
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = t.release();
     JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_t4_create_synth(jues_ctx* ctx, int64_t nao, uint64_t seed, double scale, jues_t4** out) {
+    JUES_API_BEGIN(ctx)
+    JUES_REQUIRE(out != nullptr && nao > 0, "bad arguments");
+    std::unique_ptr<jues_t4> t(new jues_t4());
+    t->ctx = ctx;
+    for (int q = 0; q < 4; ++q) { t->d[q] = nao; t->dp[q] = round_up(nao, 2); }
+    t->virtual_synth = true;
+    t->seed = seed;
+    t->scale = scale;
+    *out = t.release();
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_get_comm_counters(jues_ctx* ctx, int64_t* collectives, double* bytes_received) {
+    if (!ctx) return JUES_B200_EINVAL;
+    if (collectives) *collectives = ctx->stats.collectives;
+    if (bytes_received) *bytes_received = ctx->stats.collective_bytes;
+    return JUES_B200_OK;
 }
 
 extern "C" int jues_b200_t4_destroy(jues_t4* t) {
@@ -308,7 +343,7 @@ extern "C" int jues_b200_t4_fill(jues_t4* t, double value) {
 
 namespace {
 void check_range(const jues_t4* t, const int64_t lo[4], const int64_t hi[4], int64_t ext[4]) {
-    JUES_REQUIRE(t && t->p && lo && hi, "null argument");
+    JUES_REQUIRE(t && (t->p || t->virtual_synth) && lo && hi, "null argument");
     for (int q = 0; q < 4; ++q) {
         JUES_REQUIRE(lo[q] >= 0 && hi[q] <= t->d[q] && lo[q] <= hi[q], "slice out of range");
         ext[q] = hi[q] - lo[q];
@@ -323,6 +358,7 @@ extern "C" int jues_b200_t4_set_slice(jues_t4* t, const int64_t lo[4], const int
     int64_t ext[4];
     check_range(t, lo, hi, ext);
     JUES_REQUIRE(host != nullptr, "null host buffer");
+    if (t->virtual_synth) throw Error(JUES_B200_ESTATE, "a synthetic (generated) tensor is read-only");
     const size_t n = (size_t)(ext[0] * ext[1] * ext[2] * ext[3]);
     if (n) {
         DBuf tmp(ctx, n);
@@ -343,8 +379,17 @@ extern "C" int jues_b200_t4_get_slice(const jues_t4* t, const int64_t lo[4], con
     JUES_REQUIRE(host != nullptr, "null host buffer");
     const size_t n = (size_t)(ext[0] * ext[1] * ext[2] * ext[3]);
     if (n) {
-        DBuf tmp(ctx, n);
-        const double* src = t->p + lo[0] + t->dp[0] * (lo[1] + t->dp[1] * (lo[2] + t->dp[2] * lo[3]));
+        DBuf tmp(ctx, n), gen;
+        const double* src;
+        if (t->virtual_synth) {
+            // generate the sigma planes the slice touches, then cut the block out of them
+            const int64_t np = t->dp[0];
+            gen.alloc(ctx, (size_t)(np * np * np * ext[3]));
+            synth_eri_fill(ctx, gen.p, t->d[0], np, lo[3], ext[3], t->seed, t->scale);
+            src = gen.p + lo[0] + np * (lo[1] + np * lo[2]);
+        } else {
+            src = t->p + lo[0] + t->dp[0] * (lo[1] + t->dp[1] * (lo[2] + t->dp[2] * lo[3]));
+        }
         block_copy(ctx, src, t->dp, tmp.p, ext, ext);
         JUES_CUDA(cudaMemcpyAsync(host, tmp.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
         JUES_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -357,6 +402,7 @@ extern "C" int jues_b200_t4_synth_eri(jues_t4* t, uint64_t seed, double scale) {
     jues_ctx* ctx = t->ctx;
     JUES_API_BEGIN(ctx)
     check_t4_is_gao(t);
+    if (t->virtual_synth) throw Error(JUES_B200_ESTATE, "a synthetic (generated) tensor is read-only");
     synth_eri_fill(ctx, t->p, t->d[0], t->dp[0], 0, t->dp[3], seed, scale);
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     JUES_API_END(ctx)

@@ -14,6 +14,7 @@
 //       the orbital-energy denominator (Dijab is never materialised).
 // Every contraction below is one launch of the TMA + DMMA GEMM (contract.cu).
 #include "cc.h"
+#include "dist.h"
 
 #include <algorithm>
 #include <cmath>
@@ -25,7 +26,8 @@ void setup_problem(jues_ctx* ctx, Problem& P, int64_t nao, const double* Cao, in
     JUES_REQUIRE(nao > 0 && nocc > 0 && nvir > 0, "nao, nocc and nvir must be positive");
     JUES_REQUIRE(Cao && Cav && eps, "null orbital data");
     P.nao = nao; P.nocc = nocc; P.nvir = nvir;
-    P.np = round_up(nao, 2); P.o = round_up(nocc, 2); P.v = round_up(nvir, 2);
+    // v is padded to a multiple of 2*nranks so that the virtual index splits into equal even slabs
+    P.np = round_up(nao, 2); P.o = round_up(nocc, 2); P.v = round_up(nvir, 2 * (int64_t)ctx->nranks);
     upload_padded_matrix(ctx, P.Co, Cao, nao, nocc, P.np, P.o);
     upload_padded_matrix(ctx, P.Cv, Cav, nao, nvir, P.np, P.v);
     double emin = eps[0], emax = eps[0];
@@ -61,48 +63,79 @@ double rmp2_dev(jues_ctx* ctx, Problem& P, GaoSource& gao) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// view of the last-index slab [b0, b0+n) of a dense tensor
+Ten last_slab(const Ten& X, int64_t b0, int64_t n) {
+    Ten r = X;
+    int64_t lead = 1;
+    for (int q = 0; q + 1 < X.rank; ++q) lead *= X.d[q];
+    r.p = X.p + b0 * lead;
+    r.d[X.rank - 1] = n;
+    return r;
+}
+
+// One rank's share of the RCCD / RCCSD problem.  The output virtual index b of T2new[i,j,a,b] is
+// split into equal slabs; this rank owns b in [b0, b0+vs) (everything when nranks == 1).
+// tests/sharded_model.py is the numpy statement of exactly this algorithm (checked against the
+// oracle with 2 and 3 gloo ranks on the CPU).
 struct CC {
     jues_ctx* ctx;
     Problem& P;
     bool singles;
-    int64_t o, v;
-    // unique integral classes (physicists' order, names as in the reference)
-    DTen V, J, ooov, ovvv, oooo, vvvv;
+    int64_t o, v, b0, vs;
+    // replicated integral classes (physicists' order, names as in the reference)
+    DTen V, J, ooov, oooo;
+    // last-index slabs of the large classes:  W4[e,f,a,b] = <ef|ab>,  OA[e,f,m,b] = <ef|mb>
+    // (= ovvv[m,b,e,f]),  OB[a,j,e,b] = <aj|eb> (= (ae|jb)),  b in the slab
+    DTen W4, OA, OB;
     // static combinations
-    DTen Vt, ovvo, oovo, ooov_t, Ot;
-    // amplitudes
+    DTen Vt, oovo, ooov_t;
+    // amplitudes (replicated)
     DTen T1, T2, T1n, T2n;
 
-    CC(jues_ctx* c, Problem& p, bool s) : ctx(c), P(p), singles(s), o(p.o), v(p.v) {}
+    CC(jues_ctx* c, Problem& p, bool s) : ctx(c), P(p), singles(s), o(p.o), v(p.v) { slab_of(c, v, &b0, &vs); }
 
-    void klass(GaoSource& gphys, DTen& out, const char* slots) {
+    void klass(GaoSource& gphys, DTen& out, const char* slots, bool slab4) {
         const double* Cm[4];
         int64_t dp[4];
         for (int q = 0; q < 4; ++q) {
             Cm[q] = slots[q] == 'o' ? P.Co.p : P.Cv.p;
             dp[q] = slots[q] == 'o' ? o : v;
         }
+        if (slab4) {
+            Cm[3] = P.Cv.p + b0 * gphys.np;   // columns [b0, b0+vs) of Cav
+            dp[3] = vs;
+        }
         out.alloc(ctx, dp[0], dp[1], dp[2], dp[3]);
         tei_transform_dev(ctx, gphys, Cm, dp, out.p());
     }
 
+    void all_classes(GaoSource& gphys) {
+        klass(gphys, V, "oovv", false);
+        klass(gphys, J, "ovov", false);
+        klass(gphys, oooo, "oooo", false);
+        klass(gphys, W4, "vvvv", true);
+        if (singles) {
+            klass(gphys, ooov, "ooov", false);
+            klass(gphys, OA, "vvov", true);
+            klass(gphys, OB, "vovv", true);
+        }
+    }
+
     void build_integrals(GaoSource& gao) {
-        JUES_REQUIRE(gao.resident(), "coupled cluster needs the AO integrals resident on the device");
-        const int64_t np = gao.np;
         {
             Timer t(ctx, "cc.transform");
-            // g'[mu,lam,nu,sig] = g[mu,nu,lam,sig]: transforming g' slot by slot yields <pq|rs> directly
-            DTen gp(ctx, np, np, np, np);
-            Ten g(const_cast<double*>(gao.base()), np, np, np, np);
-            permute_axpby(ctx, 1.0, g, "mnls", 0.0, gp, "mlns");
-            DeviceGao gphys(gp.p(), gao.n, np);
-            klass(gphys, V, "oovv");
-            klass(gphys, J, "ovov");
-            klass(gphys, oooo, "oooo");
-            klass(gphys, vvvv, "vvvv");
-            if (singles) {
-                klass(gphys, ooov, "ooov");
-                klass(gphys, ovvv, "ovvv");
+            // transforming g'[mu,lam,nu,sig] = g[mu,nu,lam,sig] slot by slot yields <pq|rs> directly
+            if (gao.resident()) {
+                const int64_t np = gao.np;
+                DTen gp(ctx, np, np, np, np);
+                Ten g(const_cast<double*>(gao.base()), np, np, np, np);
+                permute_axpby(ctx, 1.0, g, "mnls", 0.0, gp, "mlns");
+                DeviceGao gphys(gp.p(), gao.n, np);
+                all_classes(gphys);
+            } else {
+                gao.phys = true;     // slabs are produced in [mu,lam,nu,sig] order
+                all_classes(gao);
+                gao.phys = false;
             }
         }
         Timer t(ctx, "cc.static");
@@ -110,17 +143,12 @@ struct CC {
         Vt.alloc(ctx, o, o, v, v);
         axpby(ctx, n2, 2.0, V.p(), 0.0, Vt.p());
         permute_axpby(ctx, -1.0, V, "ijab", 1.0, Vt, "jiab");          // Vt = 2V - V(ji)
-        ovvo.alloc(ctx, o, v, v, o);
-        permute_axpby(ctx, 1.0, V, "mjeb", 0.0, ovvo, "mbej");          // <mb|ej> = <mj|eb>
         if (singles) {
             oovo.alloc(ctx, o, o, v, o);
             permute_axpby(ctx, 1.0, ooov, "nmje", 0.0, oovo, "mnej");   // <mn|ej> = <nm|je>
             ooov_t.alloc(ctx, o, o, o, v);
             axpby(ctx, (size_t)(o * o * o * v), 2.0, ooov.p(), 0.0, ooov_t.p());
             permute_axpby(ctx, -1.0, ooov, "mnie", 1.0, ooov_t, "nmie");
-            Ot.alloc(ctx, o, v, v, v);
-            axpby(ctx, (size_t)(o * v * v * v), -1.0, ovvv.p(), 0.0, Ot.p());
-            permute_axpby(ctx, 2.0, ovvv, "mafe", 1.0, Ot, "maef");     // 2 <am|ef> - <ma|ef>
         }
     }
 
@@ -144,6 +172,8 @@ struct CC {
     void iterate() {
         const size_t n2 = (size_t)(o * o * v * v);
         const Ten t = T1, T = T2;
+        const Ten tS = last_slab(t, b0, vs), T_S = last_slab(T, b0, vs);
+        const Ten V_S = last_slab(V, b0, vs), Vt_S = last_slab(Vt, b0, vs), J_S = last_slab(J, b0, vs);
         DTen tau, tauh, Tt;
         Tt.alloc(ctx, o, o, v, v);
         axpby(ctx, n2, 2.0, T.p, 0.0, Tt.p());
@@ -155,82 +185,96 @@ struct CC {
             tau_build(ctx, T.p, t.p, 0.5, tauh.p(), o, v);
             tauv = tau; tauhv = tauh;
         }
-        // ---- one- and two-index intermediates --------------------------------------------------
-        DTen Fme(ctx, o, v), Fae(ctx, v, v), Fmi(ctx, o, o), Wpp(ctx, o, o, o, o);
-        contract(ctx, -1.0, tauhv, "mnaf", Vt, "mnef", 0.0, Fae, "ae");
-        contract(ctx, 1.0, Vt, "mnef", tauhv, "inef", 0.0, Fmi, "mi");
-        axpby(ctx, (size_t)(o * o * o * o), 1.0, oooo.p(), 0.0, Wpp.p());
-        contract(ctx, 1.0, V, "mnef", tauv, "ijef", 1.0, Wpp, "mnij");   // + 2X
-        DTen Fae_t, Fmi_t;
+        const Ten tau_S = last_slab(tauv, b0, vs), tauh_S = last_slab(tauhv, b0, vs);
+
+        // ---- small intermediates: partial sums over f in the slab, one all-reduce -------------------
+        const int64_t nFae = v * v, nFmi = o * o, nW = o * o * o * o, nR1 = o * v;
+        DBuf small(ctx, (size_t)(nFae + nFmi + nW + nR1));
+        Ten FaeT(small.p, v, v), Fmi(small.p + nFae, o, o), Wpp(small.p + nFae + nFmi, o, o, o, o),
+            R1(small.p + nFae + nFmi + nW, o, v);
+        contract(ctx, -1.0, tauh_S, "mnaf", Vt_S, "mnef", 0.0, FaeT, "ea");          // stored [e,a]
+        contract(ctx, 1.0, Vt_S, "mnef", tauh_S, "inef", 0.0, Fmi, "mi");
+        contract(ctx, 1.0, V_S, "mnef", tau_S, "ijef", 0.0, Wpp, "mnij");            // 2X
         if (singles) {
+            contract(ctx, 2.0, OB, "amef", tS, "mf", 1.0, FaeT, "ea");
+            contract(ctx, -1.0, OA, "eamf", tS, "mf", 1.0, FaeT, "ea");
+            contract(ctx, -1.0, T_S, "mnae", last_slab(ooov_t, b0, vs), "mnie", 0.0, R1, "ia");
+            contract(ctx, 2.0, T_S, "imef", OB, "amef", 1.0, R1, "ia");
+            contract(ctx, -1.0, T_S, "imef", OA, "eamf", 1.0, R1, "ia");
+        } else {
+            fill(ctx, R1.p, (size_t)nR1, 0.0);
+        }
+        all_reduce_sum(ctx, small.p, small.n);
+        axpby(ctx, (size_t)nW, 1.0, oooo.p(), 1.0, Wpp.p);
+        DTen Fme, FaeT_t, Fmi_t;
+        Ten FaeTt = FaeT, FmiT = Fmi;
+        if (singles) {
+            Fme.alloc(ctx, o, v);
             contract(ctx, 1.0, Vt, "mnef", t, "nf", 0.0, Fme, "me");
-            contract(ctx, 1.0, Ot, "maef", t, "mf", 1.0, Fae, "ae");
             contract(ctx, 1.0, ooov_t, "mnie", t, "ne", 1.0, Fmi, "mi");
-            Fae_t.alloc(ctx, v, v); Fmi_t.alloc(ctx, o, o);
-            axpby(ctx, (size_t)(v * v), 1.0, Fae.p(), 0.0, Fae_t.p());
-            contract(ctx, -0.5, t, "mb", Fme, "me", 1.0, Fae_t, "be");
-            axpby(ctx, (size_t)(o * o), 1.0, Fmi.p(), 0.0, Fmi_t.p());
-            contract(ctx, 0.5, Fme, "me", t, "je", 1.0, Fmi_t, "mj");
             contract(ctx, 1.0, ooov, "mnie", t, "je", 1.0, Wpp, "mnij");
             contract(ctx, 1.0, oovo, "mnej", t, "ie", 1.0, Wpp, "mnij");
-        }
-        const Ten FaeT = singles ? (Ten)Fae_t : (Ten)Fae;
-        const Ten FmiT = singles ? (Ten)Fmi_t : (Ten)Fmi;
-        // ---- ring intermediates ------------------------------------------------------------------
-        DTen WmBeJ(ctx, o, v, v, o), WmBEj(ctx, o, v, v, o);
-        axpby(ctx, n2, 1.0, ovvo.p(), 0.0, WmBeJ.p());
-        permute_axpby(ctx, -1.0, J, "mbje", 0.0, WmBEj, "mbej");
-        contract(ctx, 0.5, Vt, "mnef", T, "njfb", 1.0, WmBeJ, "mbej");
-        if (singles) {
-            DTen Tp2(ctx, o, o, v, v), Tph(ctx, o, o, v, v);
-            tau_build(ctx, T.p, t.p, 2.0, Tp2.p(), o, v);                // T + 2 tt
-            axpby(ctx, n2, 0.5, T.p, 0.0, Tph.p());
-            tau_build(ctx, Tph.p(), t.p, 1.0, Tph.p(), o, v);            // T/2 + tt
-            contract(ctx, -0.5, V, "mnef", Tp2, "jnfb", 1.0, WmBeJ, "mbej");
-            contract(ctx, 1.0, V, "nmef", Tph, "jnfb", 1.0, WmBEj, "mbej");
-            contract(ctx, 1.0, ovvv, "mbef", t, "jf", 1.0, WmBeJ, "mbej");
-            contract(ctx, -1.0, oovo, "mnej", t, "nb", 1.0, WmBeJ, "mbej");
-            contract(ctx, -1.0, ovvv, "mbfe", t, "jf", 1.0, WmBEj, "mbej");
-            contract(ctx, 1.0, oovo, "nmej", t, "nb", 1.0, WmBEj, "mbej");
-        } else {
-            contract(ctx, -0.5, V, "mnef", T, "jnfb", 1.0, WmBeJ, "mbej");
-            contract(ctx, 0.5, V, "nmef", T, "jnfb", 1.0, WmBEj, "mbej");
-        }
-        // ---- T1 (RCCSD.jl:248-259) -----------------------------------------------------------------
-        if (singles) {
-            DTen R1(ctx, o, v);
-            contract(ctx, 1.0, t, "ie", Fae, "ae", 0.0, R1, "ia");
+            // ---- T1 (RCCSD.jl:248-259) --------------------------------------------------------------
+            contract(ctx, 1.0, t, "ie", FaeT, "ea", 1.0, R1, "ia");
             contract(ctx, -1.0, Fmi, "mi", t, "ma", 1.0, R1, "ia");
             contract(ctx, 1.0, Tt, "imae", Fme, "me", 1.0, R1, "ia");
             contract(ctx, 2.0, V, "imae", t, "me", 1.0, R1, "ia");
             contract(ctx, -1.0, J, "maie", t, "me", 1.0, R1, "ia");
-            contract(ctx, -1.0, ooov_t, "mnie", T, "mnae", 1.0, R1, "ia");
-            contract(ctx, 1.0, T, "imef", Ot, "maef", 1.0, R1, "ia");
-            divide_Dia(ctx, R1.p(), T1n.p(), P.eo.p, P.ev.p, o, v);
+            divide_Dia(ctx, R1.p, T1n.p(), P.eo.p, P.ev.p, o, v);
+            FaeT_t.alloc(ctx, v, v); Fmi_t.alloc(ctx, o, o);
+            axpby(ctx, (size_t)nFae, 1.0, FaeT.p, 0.0, FaeT_t.p());
+            contract(ctx, -0.5, Fme, "me", t, "mb", 1.0, FaeT_t, "eb");
+            axpby(ctx, (size_t)nFmi, 1.0, Fmi.p, 0.0, Fmi_t.p());
+            contract(ctx, 0.5, Fme, "me", t, "je", 1.0, Fmi_t, "mj");
+            FaeTt = FaeT_t; FmiT = Fmi_t;
         }
-        // ---- T2: ladders --------------------------------------------------------------------------------
-        DTen Lpp(ctx, o, o, v, v), Lhh(ctx, o, o, v, v), H(ctx, o, o, v, v);
-        contract(ctx, 1.0, tauv, "ijef", vvvv, "abef", 0.0, Lpp, "ijab");
-        contract(ctx, 1.0, Wpp, "mnij", tauv, "mnab", 0.0, Lhh, "ijab");
-        // ---- T2: half residual H (its (ij)(ab) image is added by residual_finish) -------------------
-        contract(ctx, 1.0, T, "ijae", FaeT, "be", 0.0, H, "ijab");
-        contract(ctx, -1.0, T, "imab", FmiT, "mj", 1.0, H, "ijab");
-        contract(ctx, 1.0, Tt, "imae", WmBeJ, "mbej", 1.0, H, "ijab");
-        contract(ctx, 1.0, T, "imae", WmBEj, "mbej", 1.0, H, "ijab");
-        contract(ctx, 1.0, T, "mibe", WmBEj, "maej", 1.0, H, "ijab");
+        // ---- ring intermediates for the slab, layout [m,e,j,b] ------------------------------------
+        const size_t ns = (size_t)(o * o * v * vs);
+        DTen WJ(ctx, o, v, o, vs), WE(ctx, o, v, o, vs);
+        permute_axpby(ctx, 1.0, V_S, "mjeb", 0.0, WJ, "mejb");                       // <mb|ej> = <mj|eb>
+        axpby(ctx, ns, -1.0, J_S.p, 0.0, WE.p());                                      // -<mb|je> = -(mj|eb)
+        contract(ctx, 0.5, Vt, "mnef", T_S, "njfb", 1.0, WJ, "mejb");
         if (singles) {
-            DTen Yp(ctx, o, o, o, v);
-            contract(ctx, 1.0, tauv, "ijef", ovvv, "mbef", 0.0, Yp, "ijmb");
-            contract(ctx, -1.0, Yp, "ijmb", t, "ma", 1.0, H, "ijab");
-            DTen Z1(ctx, v, v, v, o), Z2(ctx, v, v, o, v);
-            contract(ctx, 1.0, t, "ma", ovvo, "mbej", 0.0, Z1, "abej");
-            contract(ctx, -1.0, t, "ie", Z1, "abej", 1.0, H, "ijab");
-            contract(ctx, 1.0, t, "mb", J, "maje", 0.0, Z2, "baje");
-            contract(ctx, -1.0, t, "ie", Z2, "baje", 1.0, H, "ijab");
-            contract(ctx, 1.0, t, "ie", ovvv, "jabe", 1.0, H, "ijab");
-            contract(ctx, -1.0, t, "ma", ooov, "mjib", 1.0, H, "ijab");
+            DTen Tp2(ctx, o, o, v, v), Tph(ctx, o, o, v, v);
+            tau_build(ctx, T.p, t.p, 2.0, Tp2.p(), o, v);                             // T + 2 tt
+            axpby(ctx, n2, 0.5, T.p, 0.0, Tph.p());
+            tau_build(ctx, Tph.p(), t.p, 1.0, Tph.p(), o, v);                         // T/2 + tt
+            contract(ctx, -0.5, V, "mnef", last_slab(Tp2, b0, vs), "jnfb", 1.0, WJ, "mejb");
+            contract(ctx, 1.0, V, "nmef", last_slab(Tph, b0, vs), "jnfb", 1.0, WE, "mejb");
+            contract(ctx, 1.0, OA, "efmb", t, "jf", 1.0, WJ, "mejb");
+            contract(ctx, -1.0, oovo, "mnej", tS, "nb", 1.0, WJ, "mejb");
+            contract(ctx, -1.0, OA, "femb", t, "jf", 1.0, WE, "mejb");
+            contract(ctx, 1.0, oovo, "nmej", tS, "nb", 1.0, WE, "mejb");
+        } else {
+            contract(ctx, -0.5, V, "mnef", T_S, "jnfb", 1.0, WJ, "mejb");
+            contract(ctx, 0.5, V, "nmef", T_S, "jnfb", 1.0, WE, "mejb");
         }
-        residual_finish(ctx, V.p(), Lpp.p(), Lhh.p(), H.p(), T2n.p(), P.eo.p, P.ev.p, o, v);
+        // ---- ladders ---------------------------------------------------------------------------------
+        DTen Lpp(ctx, o, o, v, vs), Lhh(ctx, o, o, v, vs), Hfull(ctx, o, o, v, v);
+        const Ten H = last_slab(Hfull, b0, vs);
+        contract(ctx, 1.0, tauv, "ijef", W4, "efab", 0.0, Lpp, "ijab");
+        contract(ctx, 1.0, Wpp, "mnij", tau_S, "mnab", 0.0, Lhh, "ijab");
+        // ---- half residual H for the slab (its (ij)(ab) image is added by residual_finish) ----------
+        contract(ctx, 1.0, T, "ijae", last_slab(FaeTt, b0, vs), "eb", 0.0, H, "ijab");
+        contract(ctx, -1.0, T_S, "imab", FmiT, "mj", 1.0, H, "ijab");
+        contract(ctx, 1.0, Tt, "imae", WJ, "mejb", 1.0, H, "ijab");
+        contract(ctx, 1.0, T, "imae", WE, "mejb", 1.0, H, "ijab");
+        contract(ctx, 1.0, T, "mjae", WE, "meib", 1.0, H, "ijab");    // image of T[mibe] WmBEj[maej]
+        if (singles) {
+            DTen Yp(ctx, o, o, o, vs);
+            contract(ctx, 1.0, tauv, "ijef", OA, "efmb", 0.0, Yp, "ijmb");
+            contract(ctx, -1.0, Yp, "ijmb", t, "ma", 1.0, H, "ijab");
+            DTen Z(ctx, v, o, v, vs);
+            contract(ctx, 1.0, t, "ma", V_S, "mjeb", 0.0, Z, "ajeb");
+            contract(ctx, 1.0, tS, "mb", J, "maje", 1.0, Z, "ajeb");
+            contract(ctx, 1.0, t, "ie", OB, "ajeb", 1.0, H, "ijab");
+            contract(ctx, -1.0, t, "ie", Z, "ajeb", 1.0, H, "ijab");
+            contract(ctx, -1.0, t, "ma", last_slab(ooov, b0, vs), "mjib", 1.0, H, "ijab");
+        }
+        all_gather_inplace(ctx, Hfull.p(), ns);
+        const Ten Tn_S = last_slab(T2n, b0, vs);
+        residual_finish(ctx, V_S.p, Lpp.p(), Lhh.p(), H.p, Hfull.p(), Tn_S.p, P.eo.p, P.ev.p, o, v, b0, vs);
+        all_gather_inplace(ctx, T2n.p(), ns);
         std::swap(T2.buf, T2n.buf); std::swap(T2.t, T2n.t);
         if (singles) { std::swap(T1.buf, T1n.buf); std::swap(T1.t, T1n.t); }
     }

@@ -1,21 +1,121 @@
-// Multi-GPU plumbing: one process per GPU, NCCL loaded at run time (dlopen) so that the library
-// has no link-time dependency on a particular NCCL build.
+// Multi-GPU plumbing: one process per GPU.  NCCL is loaded at run time (dlopen) so the library has
+// no link-time dependency on a particular NCCL build; a process that already loaded NCCL (e.g.
+// through torch.distributed) gets that same copy.  The collectives of the path:
+// all-gather of the half residual and of the new T2 slab, sum-all-reduce of small partials.
+#include "dist.h"
 #include "api_util.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 namespace jues {
-void dist_teardown(jues_ctx* ctx) { (void)ctx; }
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+
+void load_nccl() {
+    if (g_nccl.handle) return;
+    const char* names[] = {getenv("JUES_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    std::string tried;
+    for (const char* n : names) {
+        if (!n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+        tried += std::string(n) + " (" + dlerror() + "); ";
+    }
+    if (!h) throw Error(JUES_B200_ENCCL, "cannot load NCCL: " + tried);
+    auto sym = [&](const char* s) {
+        void* p = dlsym(h, s);
+        if (!p) throw Error(JUES_B200_ENCCL, std::string("NCCL symbol missing: ") + s);
+        return p;
+    };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+    g_nccl.handle = h;
+}
+
+void nccl_check(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess)
+        throw Error(JUES_B200_ENCCL, std::string(what) + ": " + g_nccl.GetErrorString(r));
+}
+
+}  // namespace
+
+void dist_teardown(jues_ctx* ctx) {
+    if (ctx->nccl_comm && g_nccl.handle) {
+        g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+}
+
+void all_gather_inplace(jues_ctx* ctx, double* full, size_t count_per_rank) {
+    if (ctx->nranks == 1) return;
+    // rank r's slab already sits at full + r*count_per_rank (in-place all-gather)
+    nccl_check(g_nccl.AllGather(full + (size_t)ctx->rank * count_per_rank, full, count_per_rank, ncclDouble,
+                                (ncclComm_t)ctx->nccl_comm, ctx->stream),
+               "ncclAllGather");
+    ctx->stats.collectives++;
+    ctx->stats.collective_bytes += (double)count_per_rank * 8.0 * (ctx->nranks - 1);
+}
+
+void all_reduce_sum(jues_ctx* ctx, double* buf, size_t count) {
+    if (ctx->nranks == 1) return;
+    nccl_check(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream),
+               "ncclAllReduce");
+    ctx->stats.collectives++;
+    ctx->stats.collective_bytes += (double)count * 8.0;
+}
+
 }  // namespace jues
 
+using namespace jues;
+
 extern "C" int jues_b200_nccl_unique_id(unsigned char id_out[128]) {
-    (void)id_out;
-    return JUES_B200_ENCCL;
+    if (!id_out) return JUES_B200_EINVAL;
+    try {
+        load_nccl();
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        ncclUniqueId id;
+        nccl_check(g_nccl.GetUniqueId(&id), "ncclGetUniqueId");
+        memcpy(id_out, &id, 128);
+        return JUES_B200_OK;
+    } catch (const Error& e) {
+        g_init_error = e.what();
+        return e.code;
+    }
 }
+
 extern "C" int jues_b200_init_dist(jues_ctx* ctx, int rank, int nranks, const unsigned char id[128]) {
-    (void)id;
-    if (!ctx) return JUES_B200_EINVAL;
+    JUES_API_BEGIN(ctx)
+    JUES_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    dist_teardown(ctx);
     ctx->rank = rank;
     ctx->nranks = nranks;
-    if (nranks == 1) return JUES_B200_OK;
-    ctx->last_error = "multi-GPU not implemented yet";
-    return JUES_B200_ENCCL;
+    if (nranks > 1) {
+        JUES_REQUIRE(id != nullptr, "null NCCL unique id");
+        load_nccl();
+        ncclUniqueId uid;
+        memcpy(&uid, id, 128);
+        ncclComm_t comm;
+        nccl_check(g_nccl.CommInitRank(&comm, nranks, uid, rank), "ncclCommInitRank");
+        ctx->nccl_comm = comm;
+    }
+    JUES_API_END(ctx)
 }

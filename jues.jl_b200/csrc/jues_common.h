@@ -60,6 +60,8 @@ struct Stats {
     double gemm_flops = 0;       // 2*M*N*K*batch summed over launches (padded dims)
     long long gemm_launches = 0;
     long long aux_launches = 0;  // permute / elementwise / reduction kernels
+    long long collectives = 0;   // NCCL calls
+    double collective_bytes = 0; // bytes received per rank in collectives
     void reset() { *this = Stats(); }
 };
 
@@ -98,6 +100,9 @@ struct jues_t4 {
     int64_t dp[4] = {0, 0, 0, 0};  // padded (even) extents of the device allocation
     double* p = nullptr;
     size_t bytes = 0;
+    bool virtual_synth = false;      // no storage: slabs generated on demand by the counter-based generator
+    unsigned long long seed = 0;
+    double scale = 0.0;
 };
 
 namespace jues {

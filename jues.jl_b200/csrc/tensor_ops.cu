@@ -167,21 +167,25 @@ __global__ void divide_Dijab_kernel(const double* __restrict__ R, double* __rest
     }
 }
 
-// Tnew = (V + L1 + L2 + H + P(H)) / D.  One block per (a,b) pair, the o x o slab of H[.,.,b,a] is
-// transposed through shared memory so that every global access is coalesced.
+// Tnew_S = (V_S + L1_S + L2_S + H_S + P(H)_S) / D for the slab b in [b0, b0+vs) of the last index.
+// *_S arrays are (o,o,v,vs) slabs; Hfull is the complete (o,o,v,v) half residual (all-gathered).
+// One block per (a,b) pair; the o x o block H[.,.,b,a] is transposed through shared memory so that
+// every global access is coalesced.
 __global__ void residual_finish_kernel(const double* __restrict__ V, const double* __restrict__ L1,
                                        const double* __restrict__ L2, const double* __restrict__ H,
-                                       double* __restrict__ Tn, const double* __restrict__ eo,
-                                       const double* __restrict__ ev, int o, int v) {
+                                       const double* __restrict__ Hfull, double* __restrict__ Tn,
+                                       const double* __restrict__ eo, const double* __restrict__ ev, int o,
+                                       int v, int b0, int vs) {
     extern __shared__ double sh[];  // o x (o+1)
     const long long oo = (long long)o * o;
-    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
-        const int a = (int)(ab % v), b = (int)(ab / v);
-        const long long base = ab * oo;
-        const long long baseT = ((long long)a * v + b) * oo;  // slab (b,a): index b + v*a
+    for (long long ab = blockIdx.x; ab < (long long)v * vs; ab += gridDim.x) {
+        const int a = (int)(ab % v), bl = (int)(ab / v);
+        const int b = b0 + bl;
+        const long long base = ab * oo;                        // slab-local (a, bl)
+        const long long baseT = ((long long)b + (long long)v * a) * oo;  // full (b, a)
         for (int e = threadIdx.x; e < oo; e += blockDim.x) {
             const int i = e % o, j = e / o;
-            sh[i * (o + 1) + j] = H[baseT + e];  // sh[i][j] = H[i,j,b,a]
+            sh[i * (o + 1) + j] = Hfull[baseT + e];  // sh[i][j] = H[i,j,b,a]
         }
         __syncthreads();
         const double dab = -ev[a] - ev[b];
@@ -277,15 +281,16 @@ __global__ void final_reduce_kernel(const double* __restrict__ partial, int n, d
 }
 
 __global__ void synth_eri_kernel(double* __restrict__ g, long long n, long long np, long long sig_lo,
-                                 long long sig_count, unsigned long long seed, double scale) {
+                                 long long sig_count, unsigned long long seed, double scale, int phys) {
     const long long total = np * np * np * sig_count;
     long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; L < total; L += stride) {
         long long r = L;
         const unsigned long long mu = r % np; r /= np;
-        const unsigned long long nu = r % np; r /= np;
-        const unsigned long long lam = r % np;
+        unsigned long long nu = r % np; r /= np;
+        unsigned long long lam = r % np;
+        if (phys) { const unsigned long long tmp = nu; nu = lam; lam = tmp; }  // g'[mu,lam,nu,sig]
         const unsigned long long sig = (unsigned long long)(r / np) + sig_lo;
         double val = 0.0;
         if (mu < (unsigned long long)n && nu < (unsigned long long)n && lam < (unsigned long long)n &&
@@ -440,7 +445,8 @@ void divide_Dijab(jues_ctx* ctx, const double* R, double* Tnew, const double* eo
 }
 
 void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const double* L2, const double* H,
-                     double* Tnew, const double* eo, const double* ev, int64_t o, int64_t v) {
+                     const double* Hfull, double* Tnew, const double* eo, const double* ev, int64_t o,
+                     int64_t v, int64_t b0, int64_t vs) {
     const size_t smem = (size_t)o * (o + 1) * sizeof(double);
     JUES_REQUIRE(smem <= 200 * 1024, "residual_finish: nocc too large for the shared-memory slab");
     static bool attr_done = false;
@@ -449,11 +455,12 @@ void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const dou
                                        200 * 1024));
         attr_done = true;
     }
-    long long blocks = (long long)v * v;
+    long long blocks = (long long)v * vs;
+    if (blocks == 0) return;
     const long long cap = (long long)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    residual_finish_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(V, L1, L2, H, Tnew, eo, ev, (int)o,
-                                                                         (int)v);
+    residual_finish_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(V, L1, L2, H, Hfull, Tnew, eo, ev,
+                                                                         (int)o, (int)v, (int)b0, (int)vs);
     AUX_LAUNCHED(ctx);
 }
 
@@ -505,10 +512,10 @@ void block_copy(jues_ctx* ctx, const double* src, const int64_t sd[4], double* d
 }
 
 void synth_eri_fill(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t sig_lo,
-                    int64_t sig_count, unsigned long long seed, double scale) {
+                    int64_t sig_count, unsigned long long seed, double scale, bool phys) {
     const size_t total = (size_t)n_padded * n_padded * n_padded * sig_count;
     synth_eri_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(g, n_logical, n_padded, sig_lo,
-                                                                        sig_count, seed, scale);
+                                                                        sig_count, seed, scale, phys ? 1 : 0);
     AUX_LAUNCHED(ctx);
 }
 

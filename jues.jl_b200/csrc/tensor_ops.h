@@ -63,9 +63,11 @@ void tau_build(jues_ctx* ctx, const double* T, const double* t1, double c, doubl
 // Tnew[i,j,a,b] = R[i,j,a,b] / (eo[i] + eo[j] - ev[a] - ev[b])       (may be in place)
 void divide_Dijab(jues_ctx* ctx, const double* R, double* Tnew, const double* eo, const double* ev,
                   int64_t o, int64_t v);
-// R = (R0 + L1 + L2 + H + P(H)) / D with P(H)[i,j,a,b] = H[j,i,b,a]; L1, L2 nullable
+// Tnew_S = (V_S + L1_S + L2_S + H_S + P(Hfull)_S) / D for the last-index slab [b0, b0+vs);
+// *_S are (o,o,v,vs) slabs, Hfull the complete (o,o,v,v) half residual; P(H)[i,j,a,b] = H[j,i,b,a].
 void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const double* L2, const double* H,
-                     double* Tnew, const double* eo, const double* ev, int64_t o, int64_t v);
+                     const double* Hfull, double* Tnew, const double* eo, const double* ev, int64_t o,
+                     int64_t v, int64_t b0, int64_t vs);
 // tnew[i,a] = R1[i,a] / (eo[i] - ev[a])
 void divide_Dia(jues_ctx* ctx, const double* R1, double* tnew, const double* eo, const double* ev,
                 int64_t o, int64_t v);
@@ -78,7 +80,7 @@ double mp2_energy(jues_ctx* ctx, const double* v, const double* eo, const double
 
 // counter-based synthetic ERIs (same function as jues.jl_b200.synth.counter_eri_element)
 void synth_eri_fill(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t sig_lo,
-                    int64_t sig_count, unsigned long long seed, double scale);
+                    int64_t sig_count, unsigned long long seed, double scale, bool phys = false);
 
 }  // namespace jues
 

@@ -15,7 +15,7 @@ namespace jues {
 const double* SynthGao::slab(jues_ctx* ctx, int64_t lo, int64_t cnt) {
     const int64_t plane = np * np * np;
     if ((int64_t)stage.n < plane * cnt) stage.alloc(ctx, (size_t)(plane * cnt));
-    synth_eri_fill(ctx, stage.p, n, np, lo, cnt, seed, scale);
+    synth_eri_fill(ctx, stage.p, n, np, lo, cnt, seed, scale, phys);
     return stage.p;
 }
 
@@ -51,7 +51,11 @@ const double* HostGao::slab(jues_ctx* ctx, int64_t lo, int64_t cnt) {
     const int64_t plane = np * np * np;
     if ((int64_t)stage.n < plane * cnt) stage.alloc(ctx, (size_t)(plane * cnt));
     upload_gao_planes(ctx, stage.p, h, n, np, lo, cnt);
-    return stage.p;
+    if (!phys) return stage.p;
+    if ((int64_t)stage2.n < plane * cnt) stage2.alloc(ctx, (size_t)(plane * cnt));
+    Ten a(stage.p, np, np, np, cnt), b(stage2.p, np, np, np, cnt);
+    permute_axpby(ctx, 1.0, a, "mnls", 0.0, b, "mlns");
+    return stage2.p;
 }
 
 void upload_padded_gao(jues_ctx* ctx, double* dst, const double* host, int64_t n, int64_t np) {

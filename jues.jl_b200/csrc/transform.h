@@ -9,6 +9,7 @@ namespace jues {
 struct GaoSource {
     int64_t n = 0;    // logical nao
     int64_t np = 0;   // padded (even) nao
+    bool phys = false; // non-resident sources: produce slabs as g'[mu,lam,nu,sig] = g[mu,nu,lam,sig]
     virtual ~GaoSource() {}
     virtual bool resident() const = 0;          // whole tensor addressable on the device
     virtual const double* base() const { return nullptr; }
@@ -27,7 +28,7 @@ struct DeviceGao : GaoSource {
 // host (caller-owned, unpadded column-major n^4) streamed through pinned staging in sigma slabs
 struct HostGao : GaoSource {
     const double* h;
-    DBuf stage;
+    DBuf stage, stage2;
     int64_t stage_cnt = 0;
     HostGao(const double* h_, int64_t n_, int64_t np_) : h(h_) { n = n_; np = np_; }
     bool resident() const override { return false; }

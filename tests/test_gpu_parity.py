@@ -243,3 +243,32 @@ def test_streamed_transform_equals_resident(ctx):
         del os.environ["JUES_B200_FORCE_STREAM"]
     assert abs(e1 - e2) <= 1e-13
     assert abs(e1 - orc.do_rmp2(wo)) <= E_TOL
+
+
+def test_virtual_synthetic_tensor_streams_like_the_dense_one(ctx):
+    """A storage-less synthetic gao (sigma slabs generated on demand, the route for nbf whose
+    N^4 does not fit) gives the same answers as the dense tensor, and matches the oracle."""
+    N, o = 14, 4
+    Cao, Cav, eps = jb.synth.orbitals(N, o, 5)
+    sc = jb.synth.counter_scale(N)
+    gv = jb.DeviceFourTensor.synth_eri(N, seed=5, scale=sc, ctx=ctx, virtual=True)
+    gd = jb.DeviceFourTensor.synth_eri(N, seed=5, scale=sc, ctx=ctx)
+    gh = jb.synth.counter_eri(N, 5, sc)
+    assert np.array_equal(gv[2:9, :, 3, 1:12], gh[2:9, :, 3, 1:12])
+    with pytest.raises(jb.JuesError):
+        gv[0, 0, 0, 0] = 1.0
+    wv = jb.Wfn(o, N - o, eps, Cao, Cav, gv)
+    wd = jb.Wfn(o, N - o, eps, Cao, Cav, gd)
+    wo = orc.Wfn(o, N - o, eps, Cao, Cav, gh)
+    import os
+    os.environ["JUES_B200_FORCE_STREAM"] = "1"       # several sigma slabs even at this size
+    try:
+        e_v = jb.RCCSD.do_rccsd(wv, ctx=ctx)
+        m_v = jb.do_rmp2(wv, ctx=ctx)
+        d_v = jb.RCCD.do_rccd(wv, ctx=ctx)
+    finally:
+        del os.environ["JUES_B200_FORCE_STREAM"]
+    assert abs(e_v - jb.RCCSD.do_rccsd(wd, ctx=ctx)) <= 1e-12
+    assert abs(e_v - orc.do_rccsd(wo)) <= E_TOL
+    assert abs(m_v - orc.do_rmp2(wo)) <= E_TOL
+    assert abs(d_v - orc.do_rccd(wo)) <= E_TOL

@@ -1,0 +1,140 @@
+"""The N>1 path on CPU: the sharded sweep (tests/sharded_model.py == the algorithm of
+csrc/cc.cu for nranks > 1) run by 2 and 3 real processes over torch.distributed/gloo, checked
+against the literal oracle; plus the host-side slab partition logic."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import jues.jl_b200 as jb
+from oracle import jues_oracle as orc
+import factorized_model as fm
+import sharded_model as sm
+
+
+def test_slab_bounds_cover_and_are_equal():
+    for v in (2, 7, 19, 100, 400, 401):
+        for P in (1, 2, 3, 4, 8):
+            vp, _, _ = sm.slab_bounds(v, P, 0)
+            assert vp >= v and vp % (2 * P) == 0 and vp - v < 2 * P
+            edges = [sm.slab_bounds(v, P, r)[1:] for r in range(P)]
+            assert edges[0][0] == 0 and edges[-1][1] == vp
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(P - 1))
+            assert len({b - a for a, b in edges}) == 1 and (edges[0][1] - edges[0][0]) % 2 == 0
+
+
+def test_c_library_uses_the_same_partition():
+    """jues.jl_b200.slab_bounds is the host-side mirror used by bench.py / the Julia shim."""
+    for v, P, r in [(19, 2, 1), (100, 8, 5), (400, 8, 7)]:
+        assert jb.slab_bounds(v, P, r) == sm.slab_bounds(v, P, r)
+
+
+def _setup(N, o, seed):
+    g, Cao, Cav, eps = jb.synth.dense_inputs(N, o, seed=seed)
+    return g, Cao, Cav, eps
+
+
+@pytest.mark.parametrize("singles", [True, False])
+def test_sharded_model_single_rank_equals_oracle(singles):
+    N, o = 11, 3
+    g, Cao, Cav, eps = _setup(N, o, 5)
+    v = N - o
+    I6 = fm.unique_integrals(g, Cao, Cav)
+    vp, b0, b1 = sm.slab_bounds(v, 1, 0)
+    R = sm.rank_integrals(sm.pad_virtuals(I6, v, vp), b0, b1)
+    eo = eps[:o]
+    ev = np.concatenate([eps[o:], np.full(vp - v, eps.max() + 1e3)])
+    D = orc.form_Dijab(o, v, eps)
+    t = np.zeros((o, vp))
+    T = np.zeros((o, o, vp, vp))
+    T[:, :, :v, :v] = I6["V"] / D
+    if singles:
+        I = orc.make_rccsd_integrals(g, Cao, Cav)
+        tr, Tr = np.zeros((o, v)), I["oovv"] / D
+    else:
+        ints = orc.make_rccd_integrals(g, Cao, Cav)
+        Tr = I6["V"] / D
+    for _ in range(4):
+        t, T = sm.sweep(R, t, T, eo, ev, b0, b1, singles=singles)
+        if singles:
+            tr, Tr = orc.rccsd_iteration(I, tr, Tr, orc.form_Dia(o, v, eps), D)
+            assert np.abs(t[:, :v] - tr).max() < 1e-14
+        else:
+            Tr = orc.rccd_iteration(Tr, ints, D)
+        assert np.abs(T[:, :, :v, :v] - Tr).max() < 1e-14
+        if vp > v:
+            assert np.abs(T[:, :, v:, :]).max() == 0.0 and np.abs(T[:, :, :, v:]).max() == 0.0
+
+
+def _worker(rank, world, port, N, o, seed, singles, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class Comm:
+            def allreduce(self, x):
+                t_ = torch.from_numpy(np.ascontiguousarray(x))
+                dist.all_reduce(t_)
+                return t_.numpy()
+
+            def allgather_last(self, x):
+                xs = np.ascontiguousarray(np.moveaxis(x, -1, 0))       # slab axis first: contiguous concat
+                parts = [torch.empty(xs.shape, dtype=torch.float64) for _ in range(world)]
+                dist.all_gather(parts, torch.from_numpy(xs))
+                return np.moveaxis(np.concatenate([p.numpy() for p in parts], axis=0), 0, -1)
+
+        g, Cao, Cav, eps = _setup(N, o, seed)
+        v = N - o
+        I6 = fm.unique_integrals(g, Cao, Cav)
+        vp, b0, b1 = sm.slab_bounds(v, world, rank)
+        R = sm.rank_integrals(sm.pad_virtuals(I6, v, vp), b0, b1)
+        eo = eps[:o]
+        ev = np.concatenate([eps[o:], np.full(vp - v, eps.max() + 1e3)])
+        D = orc.form_Dijab(o, v, eps)
+        t = np.zeros((o, vp))
+        T = np.zeros((o, o, vp, vp))
+        T[:, :, :v, :v] = I6["V"] / D
+        for _ in range(3):
+            t, T = sm.sweep(R, t, T, eo, ev, b0, b1, comm=Comm(), singles=singles)
+        if rank == 0:
+            if singles:
+                I = orc.make_rccsd_integrals(g, Cao, Cav)
+                tr, Tr = np.zeros((o, v)), I["oovv"] / D
+                for _ in range(3):
+                    tr, Tr = orc.rccsd_iteration(I, tr, Tr, orc.form_Dia(o, v, eps), D)
+                err = max(np.abs(t[:, :v] - tr).max(), np.abs(T[:, :, :v, :v] - Tr).max())
+            else:
+                ints = orc.make_rccd_integrals(g, Cao, Cav)
+                Tr = I6["V"] / D
+                for _ in range(3):
+                    Tr = orc.rccd_iteration(Tr, ints, D)
+                err = np.abs(T[:, :, :v, :v] - Tr).max()
+            q.put(float(err))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,singles", [(2, True), (2, False), (3, True)])
+def test_sharded_sweep_over_gloo(world, singles):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 11, 3, 7, singles, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) < 1e-13

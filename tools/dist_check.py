@@ -1,0 +1,50 @@
+"""Multi-GPU parity check, launched with torchrun (one rank per GPU): the sharded RCCD / RCCSD /
+RMP2 through the C ABI on every rank vs the CPU oracle (rank 0) and vs every other rank."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+import jues.jl_b200 as jb
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    ctx = jb.Context(local)
+    ctx.init_dist()
+    worst = 0.0
+    for (N, o, seed) in [(12, 3, 7), (24, 5, 2024), (31, 6, 11)]:
+        g, Cao, Cav, eps = jb.synth.dense_inputs(N, o, seed=seed)
+        w = jb.Wfn(o, N - o, eps, Cao, Cav, g)
+        h1, h2 = [], []
+        e_sd, T1, T2 = jb.RCCSD.do_rccsd(w, ctx=ctx, _return_T=True, _e_hist=h1)
+        e_d, T2d = jb.RCCD.do_rccd(w, ctx=ctx, _return_T2=True, _e_hist=h2)
+        e_mp2 = jb.do_rmp2(w, ctx=ctx)
+        # identical on every rank
+        t = torch.tensor([e_sd, e_d, e_mp2, float(np.abs(T2).sum()), float(np.abs(T1).sum())], dtype=torch.float64, device="cuda")
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert float((hi - lo).abs().max()) == 0.0, "ranks disagree"
+        if rank == 0:
+            from oracle import jues_oracle as orc
+            wo = orc.Wfn(o, N - o, eps, Cao, Cav, g)
+            ref = []
+            er, T1r, T2r = orc.do_rccsd(wo, return_T=True, callback=lambda it, e, a, b: ref.append(e))
+            errs = [abs(e_sd - er), np.abs(np.array(h1) - np.array(ref)).max(), np.abs(T1 - T1r).max(),
+                    np.abs(T2 - T2r).max()]
+            refd = []
+            edr, T2dr = orc.do_rccd(wo, return_T2=True, callback=lambda it, e, b: refd.append(e))
+            errs += [abs(e_d - edr), np.abs(np.array(h2) - np.array(refd)).max(), np.abs(T2d - T2dr).max(),
+                     abs(e_mp2 - orc.do_rmp2(wo))]
+            print(f"N={N} o={o} world={world} errs={['%.1e' % x for x in errs]} comm={ctx.comm_counters()}", flush=True)
+            worst = max(worst, max(errs[0], errs[1], errs[4], errs[5], errs[7]) / 1e-10, max(errs[2], errs[3], errs[6]) / 1e-9)
+    ok = torch.tensor([1.0 if worst <= 1.0 else 0.0], device="cuda")
+    dist.broadcast(ok, src=0)
+    if rank == 0:
+        print("DIST_PARITY", "OK" if worst <= 1.0 else "FAIL", "worst/tol=%.3g" % worst, flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if float(ok[0]) == 1.0 else 1)
+
+if __name__ == "__main__":
+    main()
