@@ -42,6 +42,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 NBF, NOCC = 120, 20
+WEAK_NVIR = {1: 100, 2: 124, 4: 152, 8: 192}   # F_alg(nocc=20, nvir) ~ N * F_alg(20, 100)
 SEED = 2024
 REF_MAXIT = 40          # RCCSD.jl:36
 
@@ -189,7 +190,9 @@ def reference_arm(args, rank):
         "s_per_iteration": t_it, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"RCCSD nbf={NBF} nocc={NOCC} nvir={v} (BASELINE config 3), synthetic counter-based ERIs",
-                   "algorithm": "reference literal: 15 tei_transforms + sweeps with materialised Wabef (numpy/OpenBLAS port)"},
+                   "algorithm": "reference literal: 15 tei_transforms + sweeps with materialised Wabef (numpy/OpenBLAS port)",
+                   "note": "the reference's CPU path does not shard: for every --gpus N it is timed on the 1-GPU workload "
+                           "(BASELINE config 3); the metric is F_alg-normalised TFLOP/s, comparable across the weak-scaling shapes"},
         "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                          "sample": f"15 literal transforms ({t_tr:.2f} s) + {n_iter} literal sweep(s) ({t_it:.2f} s each) "
                                    f"per step; do_rccsd extrapolated to {REF_MAXIT} sweeps"},
@@ -211,10 +214,24 @@ def gpu_arm(args, rank, world):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", rank=rank, world_size=world)
+    global NBF
+    # weak scaling: nocc fixed, nvir grows so that F_alg per GPU stays (approximately) that of the
+    # 1-GPU workload (BASELINE config 3); nvir is a multiple of 2*N so the slabs need no padding
+    NBF = NOCC + WEAK_NVIR.get(world, 100)
     o, v = NOCC, NBF - NOCC
     ctx = jb.Context(local)
-    g, Cao, Cav, eps, scale, keep = make_inputs(True)
+    if world > 1:
+        ctx.init_dist(rank, world)          # NCCL communicator inside the library (id via torch.distributed)
+    scale = jb.synth.counter_scale(NBF)
+    Cao, Cav, eps = jb.synth.orbitals(NBF, NOCC, SEED)
     gdev = jb.DeviceFourTensor.synth_eri(NBF, seed=SEED, scale=scale, ctx=ctx)   # inputs resident in HBM
+    # the same tensor in pinned host memory for the end-to-end leg (copied back from the device:
+    # bit-identical to synth.counter_eri, without minutes of numpy at the larger shapes)
+    keep = torch.empty(NBF ** 4, dtype=torch.float64).pin_memory()
+    g = keep.numpy().reshape((NBF,) * 4, order="F")
+    for s0 in range(0, NBF, 16):
+        s1 = min(NBF, s0 + 16)
+        g[:, :, :, s0:s1] = gdev[:, :, :, s0:s1]
     wdev = jb.Wfn(NOCC, v, eps, Cao, Cav, gdev)
     whost = jb.Wfn(NOCC, v, eps, Cao, Cav, g)
 
@@ -245,14 +262,28 @@ def gpu_arm(args, rank, world):
     launches_step = ((cnt["gemm_launches"] - c0["gemm_launches"]) + (cnt["aux_launches"] - c0["aux_launches"])) \
         / (args.warmup + args.steps)
 
-    # ---- the 4-index transform part of the metric: full tei_transform(gao, C), resident ----
-    Cfull = np.asfortranarray(np.hstack([Cao, Cav]))
-    for _ in range(2):
-        out = jb.tei_transform(gdev, Cfull, "bench", ctx=ctx)
-        out.free()
-    tt_ms = [ms for k, ms in ctx.phases() if k == "tei.transform"][0]
-    tei = {"workload": f"tei_transform(gao, C) nbf={NBF} (all four indices, 8 N^5 flop)", "ms": tt_ms,
-           "tflops": ctx.counters()["gemm_flops"] / tt_ms * 1e-9}
+    # ---- the 4-index transform part of the metric -------------------------------------------------
+    # (a) the integral classes of the CC run (sharded: every rank transforms its virtual slab);
+    #     flops and time of the zero-sweep call above
+    tr0_ms = [ms for k, ms in ctx.phases() if k == "cc.transform"][0]
+    tr_flops = c0["gemm_flops"]
+    if dist is not None:
+        tt_ = torch.tensor([tr_flops, -tr0_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt_[0:1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(tt_[1:2], op=dist.ReduceOp.MIN)
+        tr_flops, tr0_ms = float(tt_[0]), -float(tt_[1])
+    tei = {"cc_classes": {"workload": f"7 MO classes of RCCSD (<oo|vv>,<ov|ov>,<oo|oo>,<oo|ov>,<vv|vv>,<vv|ov>,<vo|vv>) "
+                                      f"nbf={NBF}, virtual slab per rank", "ms": tr0_ms,
+                          "tflops": tr_flops / tr0_ms * 1e-9}}
+    # (b) full tei_transform(gao, C) (all four indices, 8 N^5 flop) -- single GPU
+    if world == 1:
+        Cfull = np.asfortranarray(np.hstack([Cao, Cav]))
+        for _ in range(2):
+            out = jb.tei_transform(gdev, Cfull, "bench", ctx=ctx)
+            out.free()
+        tt_ms = [ms for k, ms in ctx.phases() if k == "tei.transform"][0]
+        tei["full"] = {"workload": f"tei_transform(gao, C) nbf={NBF} (all four indices, 8 N^5 flop)", "ms": tt_ms,
+                       "tflops": ctx.counters()["gemm_flops"] / tt_ms * 1e-9}
 
     # ---- e2e: one complete do_rccsd through the C ABI from pinned HOST buffers ----------------
     e2e_t = []
@@ -267,7 +298,7 @@ def gpu_arm(args, rank, world):
     clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel, timed live (CUDA events on the library's stream) ----
-    M, Nn, K = o * o, v * v, v * v                       # particle-particle ladder tau(ij,ef) x <ab|ef>
+    M, Nn, K = o * o, v * (v // world), v * v            # pp-ladder tau(ij,ef) x <ef|ab>, this rank's slab
     ms_gemm = ctx.gemm_bench("N", "N", M, Nn, K, reps=5)
     peak, peak_src = fp64_peak()
     ach = 2.0 * M * Nn * K / ms_gemm * 1e-9
@@ -278,10 +309,15 @@ def gpu_arm(args, rank, world):
                 "sweep_frac_of_peak": flops_step / (ms_step * 1e-3) * 1e-12 / peak}
 
     # ---- max over ranks -----------------------------------------------------------------------
+    comm = ctx.comm_counters()
     if dist is not None:
         t = torch.tensor([ms_step, t_call], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, t_call = float(t[0]), float(t[1])
+        fs = torch.tensor([flops_step, c_full["gemm_flops"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(fs, op=dist.ReduceOp.SUM)      # whole-job executed flops
+        flops_step, c_full["gemm_flops"] = float(fs[0]), float(fs[1])
+        roofline["sweep_frac_of_peak"] = flops_step / (ms_step * 1e-3) * 1e-12 / (peak * world)
 
     if rank != 0:
         return
@@ -301,10 +337,16 @@ def gpu_arm(args, rank, world):
         "metric": "rccsd_iteration_fp64_tflops", "value": F_alg / (ms_step * 1e-3) * 1e-12,
         "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "s_per_iteration": ms_step * 1e-3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"RCCSD nbf={NBF} nocc={NOCC} nvir={v} (BASELINE config 3), synthetic counter-based ERIs seed={SEED}",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"RCCSD nbf={NBF} nocc={NOCC} nvir={v}"
+                               + (" (BASELINE config 3)" if world == 1 else
+                                  f" (config 3 grown for weak scaling: F_alg = {F_alg / flops_alg_rccsd(NOCC, 100):.2f} x the 1-GPU workload)")
+                               + f", synthetic counter-based ERIs seed={SEED}",
+                   "parallelism": f"virtual-index slabs over {world} GPU(s), NCCL all-gather of H and T2 + one all-reduce per sweep"
+                                  if world > 1 else "single GPU",
+                   "collectives_per_call": comm,
                    "step": "one RCCSD sweep (intermediates + T1 + T2 + energy) on device-resident data",
-                   "l2": "inputs larger than L2 (<vv|vv> 0.8 GB, amplitudes/intermediates 32 MB each, re-streamed every sweep)",
+                   "l2": "inputs larger than L2 (<vv|vv> >= 0.8 GB per GPU, amplitudes/intermediates >= 32 MB each, re-streamed every sweep)",
                    "flops_executed_per_sweep": flops_step, "F_alg_per_sweep": F_alg, "F_ref_per_sweep": flops_ref_rccsd(o, v)},
         "tei_transform": tei,
         "e2e": {"value": REF_MAXIT * F_alg / t_call * 1e-12, "unit": "TFLOP/s",
