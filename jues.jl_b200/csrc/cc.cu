@@ -46,15 +46,17 @@ void setup_problem(jues_ctx* ctx, Problem& P, int64_t nao, const double* Cao, in
 // ---------------------------------------------------------------------------------------------
 double rmp2_dev(jues_ctx* ctx, Problem& P, GaoSource& gao) {
     const int64_t o = P.o, v = P.v;
-    DTen iajb(ctx, o, v, o, v), ijab(ctx, o, o, v, v);
+    // (ia|jb) = (ia|bj): with the occupied index in the LAST slot a streamed AO tensor (contracted
+    // over sigma first) needs an N^3 x o accumulator instead of N^3 x v
+    DTen iabj(ctx, o, v, v, o), ijab(ctx, o, o, v, v);
     {
         Timer t(ctx, "mp2.transform");
-        const double* Cm[4] = {P.Co.p, P.Cv.p, P.Co.p, P.Cv.p};
-        const int64_t dp[4] = {o, v, o, v};
-        tei_transform_dev(ctx, gao, Cm, dp, iajb.p());   // (ia|jb), chemists' order
+        const double* Cm[4] = {P.Co.p, P.Cv.p, P.Cv.p, P.Co.p};
+        const int64_t dp[4] = {o, v, v, o};
+        tei_transform_dev(ctx, gao, Cm, dp, iabj.p());   // (ia|bj), chemists' order
     }
     Timer t(ctx, "mp2.energy");
-    permute_axpby(ctx, 1.0, iajb, "iajb", 0.0, ijab, "ijab");  // <ij|ab> (IntegralTransformation.jl:96-98)
+    permute_axpby(ctx, 1.0, iabj, "iabj", 0.0, ijab, "ijab");  // <ij|ab> (IntegralTransformation.jl:96-98)
     return mp2_energy(ctx, ijab.p(), P.eo.p, P.ev.p, o, v);
 }
 
@@ -106,7 +108,30 @@ struct CC {
             dp[3] = vs;
         }
         out.alloc(ctx, dp[0], dp[1], dp[2], dp[3]);
-        tei_transform_dev(ctx, gphys, Cm, dp, out.p());
+        if (gphys.resident()) {
+            tei_transform_dev(ctx, gphys, Cm, dp, out.p());
+            return;
+        }
+        // A streamed AO tensor must be contracted over its last index first, and the first quarter's
+        // output is N^3 x d4: use <pq|rs> = <rq|ps> = <ps|rq> = <qp|sr> (8 slot orders in all) to put
+        // the SMALLEST extent in the last slot, transform, and permute back.
+        static const int sym[8][4] = {{0, 1, 2, 3}, {0, 3, 2, 1}, {1, 0, 3, 2}, {1, 2, 3, 0},
+                                      {2, 1, 0, 3}, {2, 3, 0, 1}, {3, 0, 1, 2}, {3, 2, 1, 0}};
+        int best = 0;
+        for (int g = 1; g < 8; ++g)
+            if (dp[sym[g][3]] < dp[sym[best][3]]) best = g;
+        if (best == 0) {
+            tei_transform_dev(ctx, gphys, Cm, dp, out.p());
+            return;
+        }
+        const double* Cm2[4];
+        int64_t dp2[4];
+        char ly[5] = {0, 0, 0, 0, 0};
+        const char lx[5] = "pqrs";
+        for (int k = 0; k < 4; ++k) { Cm2[k] = Cm[sym[best][k]]; dp2[k] = dp[sym[best][k]]; ly[k] = lx[sym[best][k]]; }
+        DTen y(ctx, dp2[0], dp2[1], dp2[2], dp2[3]);
+        tei_transform_dev(ctx, gphys, Cm2, dp2, y.p());
+        permute_axpby(ctx, 1.0, y, ly, 0.0, out, lx);
     }
 
     void all_classes(GaoSource& gphys) {
@@ -322,9 +347,13 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
         {
             // one timed "step" = one sweep + the energy the reference evaluates every sweep
             // (RCCSD.jl:104); the energy read-back is the step's device->host result
+            const double f0 = ctx->stats.gemm_flops;
             Timer t(ctx, "cc.iteration");
             cc.iterate();
             res.e_hist[it] = cc.energy();
+            t.stop();
+            // FP64 flops this rank's GEMM launches executed in the sweep (reported as a pseudo-phase)
+            ctx->timings.emplace_back("cc.iteration.gflop", (float)((ctx->stats.gemm_flops - f0) * 1e-9));
         }
         report(it, res.e_hist[it]);
     }

@@ -149,7 +149,13 @@ void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4],
             // stream sigma slabs:  tmp[mu nu lam, b] += g[mu nu lam, slab] * C4[slab, b]
             JUES_REQUIRE(ax == 3, "internal: streamed transform must contract the last index first");
             const int64_t plane = np * np * np;
-            int64_t cnt = std::max<int64_t>(2, std::min<int64_t>(np, (int64_t)(2.0e9 / 8.0 / (double)plane)));
+            // Every slab GEMM re-reads and re-writes the whole N^3 x d4 accumulator, so K (= slab
+            // thickness) should be >= ~64 for the pass to stay compute-bound (2*cnt/16 flop per byte
+            // of accumulator traffic vs a ridge of ~5.7 flop/B); spend up to 20 % of the free HBM.
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            int64_t cnt = (int64_t)(0.20 * (double)free_b / 8.0 / (double)plane);
+            cnt = std::max<int64_t>(2, std::min<int64_t>(np, std::min<int64_t>(cnt, 128)));
             if (getenv("JUES_B200_FORCE_STREAM")) cnt = std::min<int64_t>(cnt, 6);  // testing: several slabs
             cnt &= ~int64_t(1);
             for (int64_t lo = 0; lo < np; lo += cnt) {
