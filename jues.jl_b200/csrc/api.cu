@@ -11,6 +11,8 @@ namespace {
 
 void begin_call(jues_ctx* ctx) {
     ctx->timings.clear();
+    ctx->alloc_host_s = 0.0;
+    ctx->alloc_calls = 0;
     ctx->stats.reset();
     ctx->bytes_peak = ctx->bytes_allocated;
 }
@@ -31,6 +33,7 @@ void make_host_gao(jues_ctx* ctx, HostGaoHolder& h, const double* gao, int64_t n
     JUES_REQUIRE(gao != nullptr && nao > 0, "null or empty gao");
     const int64_t np = round_up(nao, 2);
     const double bytes = (double)np * np * np * np * 8.0;
+    flush_big_cache(ctx);
     const double avail = (double)free_device_bytes() + 0.0;
     const bool force_stream = getenv("JUES_B200_FORCE_STREAM") != nullptr;  // testing hook
     // coupled cluster keeps a second, re-ordered copy next to the AO tensor: budget twice the bytes
@@ -206,6 +209,8 @@ void run_cc(jues_ctx* ctx, GaoSource& src, const double* Cao, int64_t nocc, cons
     setup_problem(ctx, P, src.n, Cao, nocc, Cav, nvir, eps);
     CCResult r = cc_dev(ctx, P, src, singles, maxit, guess_mode, T1_out, T2_out, ctx->amp_cb, ctx->amp_user);
     *e = r.energy;
+    ctx->timings.emplace_back("alloc.host_ms", (float)(ctx->alloc_host_s * 1e3));
+    ctx->timings.emplace_back("alloc.calls", (float)ctx->alloc_calls);
     if (e_hist)
         for (int k = 0; k <= maxit; ++k) e_hist[k] = r.e_hist[k];
 }
@@ -277,6 +282,11 @@ extern "C" int jues_b200_t4_create(jues_ctx* ctx, int64_t d1, int64_t d2, int64_
     for (int q = 0; q < 4; ++q) { t->d[q] = d[q]; t->dp[q] = round_up(d[q], 2); n *= (size_t)t->dp[q]; }
     t->bytes = (n * 8 + 255) & ~size_t(255);
     cudaError_t e = cudaMalloc(&t->p, t->bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        flush_big_cache(ctx);
+        e = cudaMalloc(&t->p, t->bytes);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         char buf[160];

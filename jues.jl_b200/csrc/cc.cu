@@ -93,6 +93,7 @@ struct CC {
     DTen Vt, oovo, ooov_t;
     // amplitudes (replicated)
     DTen T1, T2, T1n, T2n;
+    TransformWorkspace tws;   // shared by the class transforms, released before the sweeps
 
     CC(jues_ctx* c, Problem& p, bool s) : ctx(c), P(p), singles(s), o(p.o), v(p.v) { slab_of(c, v, &b0, &vs); }
 
@@ -109,7 +110,7 @@ struct CC {
         }
         out.alloc(ctx, dp[0], dp[1], dp[2], dp[3]);
         if (gphys.resident()) {
-            tei_transform_dev(ctx, gphys, Cm, dp, out.p());
+            tei_transform_dev(ctx, gphys, Cm, dp, out.p(), false, &tws);
             return;
         }
         // A streamed AO tensor must be contracted over its last index first, and the first quarter's
@@ -121,7 +122,7 @@ struct CC {
         for (int g = 1; g < 8; ++g)
             if (dp[sym[g][3]] < dp[sym[best][3]]) best = g;
         if (best == 0) {
-            tei_transform_dev(ctx, gphys, Cm, dp, out.p());
+            tei_transform_dev(ctx, gphys, Cm, dp, out.p(), false, &tws);
             return;
         }
         const double* Cm2[4];
@@ -130,7 +131,7 @@ struct CC {
         const char lx[5] = "pqrs";
         for (int k = 0; k < 4; ++k) { Cm2[k] = Cm[sym[best][k]]; dp2[k] = dp[sym[best][k]]; ly[k] = lx[sym[best][k]]; }
         DTen y(ctx, dp2[0], dp2[1], dp2[2], dp2[3]);
-        tei_transform_dev(ctx, gphys, Cm2, dp2, y.p());
+        tei_transform_dev(ctx, gphys, Cm2, dp2, y.p(), false, &tws);
         permute_axpby(ctx, 1.0, y, ly, 0.0, out, lx);
     }
 
@@ -163,6 +164,7 @@ struct CC {
                 gao.phys = false;
             }
         }
+        tws.buf[0].release(); tws.buf[1].release();
         Timer t(ctx, "cc.static");
         const size_t n2 = (size_t)(o * o * v * v);
         Vt.alloc(ctx, o, o, v, v);

@@ -73,6 +73,8 @@ extern "C" void jues_b200_finalize(jues_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     jues::dist_teardown(ctx);
+    for (auto& kv : ctx->big_free) cudaFree(kv.second);
+    ctx->big_free.clear();
     if (ctx->red_dev) cudaFree(ctx->red_dev);
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -11,6 +11,7 @@
 #include <vector>
 #include <map>
 #include <stdexcept>
+#include <chrono>
 
 #include "../../include/jues_b200.h"
 
@@ -83,6 +84,10 @@ struct jues_ctx {
     std::vector<std::pair<std::string, float>> timings;
     size_t bytes_allocated = 0;
     size_t bytes_peak = 0;
+    std::multimap<size_t, double*> big_free;   // cached cudaMalloc blocks (>= 64 MB) by size
+    size_t big_cached_bytes = 0;
+    double alloc_host_s = 0.0;   // host wall-clock spent inside device allocation calls (diagnostic)
+    long long alloc_calls = 0;
     // multi-GPU (one process per GPU): rank / world size and an NCCL communicator (opaque here)
     int rank = 0;
     int nranks = 1;
@@ -122,12 +127,19 @@ struct DBuf {
     DBuf& operator=(DBuf&& o) noexcept {
         if (this != &o) {
             release();
-            ctx = o.ctx; p = o.p; n = o.n;
-            o.p = nullptr; o.n = 0;
+            ctx = o.ctx; p = o.p; n = o.n; cap = o.cap;
+            o.p = nullptr; o.n = 0; o.cap = 0;
         }
         return *this;
     }
     ~DBuf() { release(); }
+    // Small blocks come from the stream-ordered pool (no device synchronisation).  Blocks of
+    // kBigBytes and more come from cudaMalloc and are cached per context by size: growing the
+    // stream-ordered pool costs ~5 ms/GB at best and seconds once multi-GB blocks of many different
+    // sizes fragment it (measured: 8 s of host time in 107 allocations of one large transform).
+    // Re-using a cached block right away is safe because all work of a context is on one stream.
+    static constexpr size_t kBigBytes = size_t(64) << 20;
+    size_t cap = 0;  // bytes actually held (big blocks may be slightly larger than requested)
     void alloc(jues_ctx* c, size_t n_) {
         release();
         ctx = c;
@@ -136,7 +148,31 @@ struct DBuf {
         // keep every allocation a multiple of 256 B so that TMA boxes that overhang the logical
         // end of a tensor never leave the allocation's page
         bytes = (bytes + 255) & ~size_t(255);
-        cudaError_t e = cudaMallocAsync((void**)&p, bytes, c->stream);  // stream-ordered pool: no device sync
+        const auto t0__ = std::chrono::steady_clock::now();
+        cudaError_t e = cudaSuccess;
+        cap = bytes;
+        if (bytes >= kBigBytes) {
+            auto it = c->big_free.lower_bound(bytes);
+            if (it != c->big_free.end() && it->first <= bytes + bytes / 8) {
+                p = it->second;
+                cap = it->first;
+                c->big_cached_bytes -= cap;
+                c->big_free.erase(it);
+            } else {
+                e = cudaMalloc((void**)&p, bytes);
+                if (e == cudaErrorMemoryAllocation) {   // give the cache back to the driver and retry
+                    cudaGetLastError();
+                    for (auto& kv : c->big_free) cudaFree(kv.second);
+                    c->big_free.clear();
+                    c->big_cached_bytes = 0;
+                    e = cudaMalloc((void**)&p, bytes);
+                }
+            }
+        } else {
+            e = cudaMallocAsync((void**)&p, bytes, c->stream);
+        }
+        c->alloc_host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0__).count();
+        c->alloc_calls++;
         if (e != cudaSuccess) {
             p = nullptr;
             char buf[256];
@@ -145,21 +181,32 @@ struct DBuf {
             cudaGetLastError();
             throw Error(JUES_B200_ENOMEM, buf);
         }
-        c->bytes_allocated += bytes;
+        c->bytes_allocated += cap;
         if (c->bytes_allocated > c->bytes_peak) c->bytes_peak = c->bytes_allocated;
     }
     void release() {
         if (p) {
-            size_t bytes = (n ? n : 1) * sizeof(double);
-            bytes = (bytes + 255) & ~size_t(255);
-            cudaFreeAsync(p, ctx->stream);
-            if (ctx) ctx->bytes_allocated -= bytes;
+            if (cap >= kBigBytes) {
+                ctx->big_free.emplace(cap, p);
+                ctx->big_cached_bytes += cap;
+            } else {
+                cudaFreeAsync(p, ctx->stream);
+            }
+            ctx->bytes_allocated -= cap;
             p = nullptr;
             n = 0;
+            cap = 0;
         }
     }
     void zero() { JUES_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream)); }
 };
+
+// give every cached large block back to the driver
+inline void flush_big_cache(jues_ctx* c) {
+    for (auto& kv : c->big_free) cudaFree(kv.second);
+    c->big_free.clear();
+    c->big_cached_bytes = 0;
+}
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -65,6 +65,16 @@ void upload_padded_gao(jues_ctx* ctx, double* dst, const double* host, int64_t n
 
 namespace {
 
+// JUES_B200_TRACE=1: per-stage CUDA-event timings of the transform (serialises the stream)
+struct TraceTimer {
+    Timer* t = nullptr;
+    TraceTimer(jues_ctx* ctx, const char* name) {
+        static const bool on = getenv("JUES_B200_TRACE") != nullptr;
+        if (on) t = new Timer(ctx, name);
+    }
+    ~TraceTimer() { delete t; }
+};
+
 double quarter_flops(const int64_t e[4], int axis, int64_t d) {
     return 2.0 * (double)e[0] * (double)e[1] * (double)e[2] * (double)e[3] * (double)d;
 }
@@ -130,12 +140,13 @@ double tei_transform_flops(int64_t np, const int64_t dp[4], bool reference_order
 }
 
 void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4], const int64_t dp[4],
-                       double* out, bool reference_order) {
+                       double* out, bool reference_order, TransformWorkspace* ws) {
     const int64_t np = gao.np;
     int order[4];
     best_order(np, dp, reference_order, !gao.resident(), order, nullptr);
     int64_t e[4] = {np, np, np, np};
-    DBuf cur, nxt;
+    TransformWorkspace local_ws;
+    TransformWorkspace* w = ws ? ws : &local_ws;   // ping/pong buffers re-used by successive transforms
     const double* src = gao.base();
     for (int s = 0; s < 4; ++s) {
         const int ax = order[s];
@@ -144,7 +155,11 @@ void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4],
         const size_t nout = (size_t)(e2[0] * e2[1] * e2[2] * e2[3]);
         double* dst;
         if (s == 3) dst = out;
-        else { nxt.alloc(ctx, nout); dst = nxt.p; }
+        else {
+            DBuf& b = w->buf[s & 1];
+            if (b.n < nout) b.alloc(ctx, nout);
+            dst = b.p;
+        }
         if (s == 0 && !gao.resident()) {
             // stream sigma slabs:  tmp[mu nu lam, b] += g[mu nu lam, slab] * C4[slab, b]
             JUES_REQUIRE(ax == 3, "internal: streamed transform must contract the last index first");
@@ -154,23 +169,27 @@ void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4],
             // of accumulator traffic vs a ridge of ~5.7 flop/B); spend up to 20 % of the free HBM.
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
-            int64_t cnt = (int64_t)(0.20 * (double)free_b / 8.0 / (double)plane);
+            free_b += ctx->big_cached_bytes;   // cached blocks are ours to re-use
+            int64_t cnt = (int64_t)(std::min(0.20 * (double)free_b, 24.0e9) / 8.0 / (double)plane);
             cnt = std::max<int64_t>(2, std::min<int64_t>(np, std::min<int64_t>(cnt, 128)));
             if (getenv("JUES_B200_FORCE_STREAM")) cnt = std::min<int64_t>(cnt, 6);  // testing: several slabs
             cnt &= ~int64_t(1);
             for (int64_t lo = 0; lo < np; lo += cnt) {
                 const int64_t c = std::min(cnt, np - lo);
-                const double* sl = gao.slab(ctx, lo, c);
+                const double* sl;
+                {
+                    TraceTimer tt(ctx, "tei.slab");
+                    sl = gao.slab(ctx, lo, c);
+                }
                 int64_t es[4] = {np, np, np, c};
+                TraceTimer tq(ctx, "tei.q1");
                 quarter(ctx, sl, es, 3, Cm[3], np, dp[3], dst, lo == 0 ? 0.0 : 1.0, lo, c);
             }
         } else {
+            TraceTimer tq(ctx, s == 0 ? "tei.q1" : s == 1 ? "tei.q2" : s == 2 ? "tei.q3" : "tei.q4");
             quarter(ctx, src, e, ax, Cm[ax], np, dp[ax], dst);
         }
-        if (s < 3) {
-            cur = std::move(nxt);
-            src = cur.p;
-        }
+        if (s < 3) src = dst;
         e[ax] = dp[ax];
     }
 }

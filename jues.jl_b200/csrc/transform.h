@@ -57,8 +57,13 @@ void upload_padded_gao(jues_ctx* ctx, double* dst, const double* host, int64_t n
 // chosen to minimise the flop count (the last AO index first when gao is streamed).
 // If `reference_order` is set the reference's fixed order (sigma, lambda, nu, mu;
 // Transformation.jl:68-91) is used.
+// Ping/pong buffers for the three intermediate quarter-transformed tensors; pass the same workspace
+// to successive transforms to avoid re-allocating multi-GB blocks for every integral class.
+struct TransformWorkspace {
+    DBuf buf[2];
+};
 void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4], const int64_t dp[4],
-                       double* out, bool reference_order = false);
+                       double* out, bool reference_order = false, TransformWorkspace* ws = nullptr);
 
 // flops of the order tei_transform_dev would pick (for reporting)
 double tei_transform_flops(int64_t np, const int64_t dp[4], bool reference_order, bool streamed);
