@@ -46,18 +46,35 @@ void setup_problem(jues_ctx* ctx, Problem& P, int64_t nao, const double* Cao, in
 // ---------------------------------------------------------------------------------------------
 double rmp2_dev(jues_ctx* ctx, Problem& P, GaoSource& gao) {
     const int64_t o = P.o, v = P.v;
-    // (ia|jb) = (ia|bj): with the occupied index in the LAST slot a streamed AO tensor (contracted
-    // over sigma first) needs an N^3 x o accumulator instead of N^3 x v
-    DTen iabj(ctx, o, v, v, o), ijab(ctx, o, o, v, v);
+    int64_t b0, vs;
+    slab_of(ctx, v, &b0, &vs);   // this rank's slab of the virtual index b (everything when nranks == 1)
+    // E = sum_{ij a b} v_ijab (2 v_ijab - v_ijba) / D with v_ijba = v_jiab: every (a, b in slab) block is
+    // self-contained, so ranks need no exchange but the final scalar.
+    // A streamed AO tensor is contracted over sigma first and its first-quarter accumulator is
+    // N^3 x (last slot): put the slab last when it is the smaller extent ((ia|j b_S): the first
+    // quarter is then sharded too), the occupied index otherwise ((ia|b_S j)).
+    const bool slab_last = gao.resident() || vs <= o;
+    DTen t4, ijab(ctx, o, o, v, vs);
     {
         Timer t(ctx, "mp2.transform");
-        const double* Cm[4] = {P.Co.p, P.Cv.p, P.Cv.p, P.Co.p};
-        const int64_t dp[4] = {o, v, v, o};
-        tei_transform_dev(ctx, gao, Cm, dp, iabj.p());   // (ia|bj), chemists' order
+        const double* CvS = P.Cv.p + b0 * gao.np;
+        if (slab_last) {
+            const double* Cm[4] = {P.Co.p, P.Cv.p, P.Co.p, CvS};
+            const int64_t dp[4] = {o, v, o, vs};
+            t4.alloc(ctx, o, v, o, vs);
+            tei_transform_dev(ctx, gao, Cm, dp, t4.p());   // (ia|jb), chemists' order
+        } else {
+            const double* Cm[4] = {P.Co.p, P.Cv.p, CvS, P.Co.p};
+            const int64_t dp[4] = {o, v, vs, o};
+            t4.alloc(ctx, o, v, vs, o);
+            tei_transform_dev(ctx, gao, Cm, dp, t4.p());   // (ia|bj) = (ia|jb)
+        }
     }
     Timer t(ctx, "mp2.energy");
-    permute_axpby(ctx, 1.0, iabj, "iabj", 0.0, ijab, "ijab");  // <ij|ab> (IntegralTransformation.jl:96-98)
-    return mp2_energy(ctx, ijab.p(), P.eo.p, P.ev.p, o, v);
+    // <ij|ab> (IntegralTransformation.jl:96-98)
+    permute_axpby(ctx, 1.0, t4, slab_last ? "iajb" : "iabj", 0.0, ijab, "ijab");
+    double e = mp2_energy(ctx, ijab.p(), P.eo.p, P.ev.p, o, v, b0, vs);
+    return all_reduce_scalar(ctx, e);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -135,13 +152,29 @@ struct CC {
         permute_axpby(ctx, 1.0, y, ly, 0.0, out, lx);
     }
 
+    // A class every rank needs in full: with a streamed AO tensor each rank transforms only its
+    // share of the sigma planes (the transform is linear) and the partial tensors are summed.
+    void replicated_klass(GaoSource& gphys, DTen& out, const char* slots) {
+        const bool split = !gphys.resident() && ctx->nranks > 1;
+        if (split) {
+            const int64_t per = round_up((gphys.np + ctx->nranks - 1) / ctx->nranks, 2);
+            gphys.sig_lo = std::min<int64_t>(gphys.np, per * ctx->rank);
+            gphys.sig_hi = std::min<int64_t>(gphys.np, per * (ctx->rank + 1));
+        }
+        klass(gphys, out, slots, false);
+        if (split) {
+            gphys.sig_lo = 0; gphys.sig_hi = -1;
+            all_reduce_sum(ctx, out.p(), (size_t)out.t.size());
+        }
+    }
+
     void all_classes(GaoSource& gphys) {
-        klass(gphys, V, "oovv", false);
-        klass(gphys, J, "ovov", false);
-        klass(gphys, oooo, "oooo", false);
+        replicated_klass(gphys, V, "oovv");
+        replicated_klass(gphys, J, "ovov");
+        replicated_klass(gphys, oooo, "oooo");
         klass(gphys, W4, "vvvv", true);
         if (singles) {
-            klass(gphys, ooov, "ooov", false);
+            replicated_klass(gphys, ooov, "ooov");
             klass(gphys, OA, "vvov", true);
             klass(gphys, OB, "vovv", true);
         }

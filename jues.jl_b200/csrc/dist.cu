@@ -83,6 +83,17 @@ void all_reduce_sum(jues_ctx* ctx, double* buf, size_t count) {
     ctx->stats.collective_bytes += (double)count * 8.0;
 }
 
+double all_reduce_scalar(jues_ctx* ctx, double x) {
+    if (ctx->nranks == 1) return x;
+    double* slot = ctx->red_dev + ctx->red_cap - 2;
+    JUES_CUDA(cudaMemcpyAsync(slot, &x, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    all_reduce_sum(ctx, slot, 1);
+    double r = 0.0;
+    JUES_CUDA(cudaMemcpyAsync(&r, slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    return r;
+}
+
 }  // namespace jues
 
 using namespace jues;

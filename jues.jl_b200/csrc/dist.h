@@ -6,6 +6,7 @@ namespace jues {
 // in-place all-gather: rank r contributed full[r*count .. (r+1)*count)
 void all_gather_inplace(jues_ctx* ctx, double* full, size_t count_per_rank);
 void all_reduce_sum(jues_ctx* ctx, double* buf, size_t count);
+double all_reduce_scalar(jues_ctx* ctx, double x);   // sum of a host scalar over ranks (blocking)
 // equal slabs of the virtual extent (v is a multiple of 2*nranks): [b0, b0+vs)
 inline void slab_of(const jues_ctx* ctx, int64_t v, int64_t* b0, int64_t* vs) {
     *vs = v / ctx->nranks;

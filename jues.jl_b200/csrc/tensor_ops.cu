@@ -3,6 +3,7 @@
 // epilogue, synthetic ERI generator).  All reductions are deterministic (fixed two-pass tree).
 #include "tensor_ops.h"
 #include "api_util.h"
+#include <algorithm>
 
 namespace jues {
 
@@ -255,18 +256,19 @@ __global__ void cc_energy_kernel(const double* __restrict__ V, const double* __r
 }
 
 __global__ void mp2_energy_kernel(const double* __restrict__ V, const double* __restrict__ eo,
-                                  const double* __restrict__ ev, int o, int v, double* __restrict__ partial) {
+                                  const double* __restrict__ ev, int o, int v, int b0, int vs,
+                                  double* __restrict__ partial) {
     const long long oo = (long long)o * o;
     double acc = 0.0;
-    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
-        const int a = (int)(ab % v), b = (int)(ab / v);
+    for (long long ab = blockIdx.x; ab < (long long)v * vs; ab += gridDim.x) {
+        const int a = (int)(ab % v), b = b0 + (int)(ab / v);
         const long long base = ab * oo;
-        const long long baseT = ((long long)b + (long long)v * a) * oo;
         const double dab = -ev[a] - ev[b];
         for (int e = threadIdx.x; e < oo; e += blockDim.x) {
             const int i = e % o, j = e / o;
             const double x = V[base + e];
-            acc += x * (2.0 * x - V[baseT + e]) / (eo[i] + eo[j] + dab);
+            // <ij|ba> = <ji|ab>: the partner lives in the same (a,b) block
+            acc += x * (2.0 * x - V[base + j + (long long)o * i]) / (eo[i] + eo[j] + dab);
         }
     }
     const double r = block_reduce<256>(acc);
@@ -494,11 +496,16 @@ double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* 
     return finish_reduction(ctx, blocks);
 }
 
-double mp2_energy(jues_ctx* ctx, const double* V, const double* eo, const double* ev, int64_t o, int64_t v) {
-    const int blocks = reduction_blocks(ctx, v);
-    mp2_energy_kernel<<<blocks, 256, 0, ctx->stream>>>(V, eo, ev, (int)o, (int)v, ctx->red_dev);
+double mp2_energy(jues_ctx* ctx, const double* V, const double* eo, const double* ev, int64_t o, int64_t v,
+                  int64_t b0, int64_t vs) {
+    long long blocks = (long long)v * vs;
+    const long long cap = std::min<long long>((long long)ctx->sm_count * 4, (long long)ctx->red_cap - 4);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    mp2_energy_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(V, eo, ev, (int)o, (int)v, (int)b0, (int)vs,
+                                                                  ctx->red_dev);
     AUX_LAUNCHED(ctx);
-    return finish_reduction(ctx, blocks);
+    return finish_reduction(ctx, (int)blocks);
 }
 
 void block_copy(jues_ctx* ctx, const double* src, const int64_t sd[4], double* dst, const int64_t dd[4],

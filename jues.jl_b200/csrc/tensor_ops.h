@@ -76,7 +76,9 @@ void divide_Dia(jues_ctx* ctx, const double* R1, double* tnew, const double* eo,
 // E = sum_{ijab} V[ijab] * (2*X[ijab] - X[jiab]),  X = T + t(x)t (t nullable)
 double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v);
 // E = sum_{ijab} v[ijab] (2 v[ijab] - v[ijba]) / (eo[i]+eo[j]-ev[a]-ev[b])
-double mp2_energy(jues_ctx* ctx, const double* v, const double* eo, const double* ev, int64_t o, int64_t vv);
+// v is the last-index slab (o,o,vv,vs) of <ij|ab>, b in [b0, b0+vs); v_ijba is taken as v_jiab
+double mp2_energy(jues_ctx* ctx, const double* v, const double* eo, const double* ev, int64_t o, int64_t vv,
+                  int64_t b0, int64_t vs);
 
 // counter-based synthetic ERIs (same function as jues.jl_b200.synth.counter_eri_element)
 void synth_eri_fill(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t sig_lo,

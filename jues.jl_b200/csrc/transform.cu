@@ -174,8 +174,10 @@ void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4],
             cnt = std::max<int64_t>(2, std::min<int64_t>(np, std::min<int64_t>(cnt, 128)));
             if (getenv("JUES_B200_FORCE_STREAM")) cnt = std::min<int64_t>(cnt, 6);  // testing: several slabs
             cnt &= ~int64_t(1);
-            for (int64_t lo = 0; lo < np; lo += cnt) {
-                const int64_t c = std::min(cnt, np - lo);
+            const int64_t s_begin = gao.sig_lo, s_end = gao.sig_hi < 0 ? np : gao.sig_hi;
+            if (s_begin >= s_end) JUES_CUDA(cudaMemsetAsync(dst, 0, nout * sizeof(double), ctx->stream));
+            for (int64_t lo = s_begin; lo < s_end; lo += cnt) {
+                const int64_t c = std::min(cnt, s_end - lo);
                 const double* sl;
                 {
                     TraceTimer tt(ctx, "tei.slab");
@@ -183,7 +185,7 @@ void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4],
                 }
                 int64_t es[4] = {np, np, np, c};
                 TraceTimer tq(ctx, "tei.q1");
-                quarter(ctx, sl, es, 3, Cm[3], np, dp[3], dst, lo == 0 ? 0.0 : 1.0, lo, c);
+                quarter(ctx, sl, es, 3, Cm[3], np, dp[3], dst, lo == s_begin ? 0.0 : 1.0, lo, c);
             }
         } else {
             TraceTimer tq(ctx, s == 0 ? "tei.q1" : s == 1 ? "tei.q2" : s == 2 ? "tei.q3" : "tei.q4");

@@ -10,6 +10,10 @@ struct GaoSource {
     int64_t n = 0;    // logical nao
     int64_t np = 0;   // padded (even) nao
     bool phys = false; // non-resident sources: produce slabs as g'[mu,lam,nu,sig] = g[mu,nu,lam,sig]
+    // non-resident sources: restrict the streamed sigma range to [sig_lo, sig_hi) (hi < 0: all).  The
+    // transform is linear in gao, so ranks that each stream a disjoint sigma range obtain partial
+    // results whose sum (one all-reduce) is the full transform.
+    int64_t sig_lo = 0, sig_hi = -1;
     virtual ~GaoSource() {}
     virtual bool resident() const = 0;          // whole tensor addressable on the device
     virtual const double* base() const { return nullptr; }
