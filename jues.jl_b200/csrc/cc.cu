@@ -111,6 +111,7 @@ struct CC {
     // amplitudes (replicated)
     DTen T1, T2, T1n, T2n;
     TransformWorkspace tws;   // shared by the class transforms, released before the sweeps
+    PermCache pcache;         // permuted operand copies (static: once; amplitude-derived: once per sweep)
 
     CC(jues_ctx* c, Problem& p, bool s) : ctx(c), P(p), singles(s), o(p.o), v(p.v) { slab_of(c, v, &b0, &vs); }
 
@@ -212,6 +213,13 @@ struct CC {
         }
     }
 
+    void register_static() {
+        ctx->perm_cache = &pcache;
+        for (DTen* t : {&V, &J, &oooo, &ooov, &Vt, &oovo, &ooov_t, &OA, &OB})
+            if (t->p()) pcache.add(t->t, false);
+    }
+    ~CC() { ctx->perm_cache = nullptr; pcache.clear(); }
+
     double energy() { return cc_energy(ctx, V.p(), T2.p(), singles ? T1.p() : nullptr, o, v); }
 
     void guess(int guess_mode) {
@@ -246,6 +254,8 @@ struct CC {
             tauv = tau; tauhv = tauh;
         }
         const Ten tau_S = last_slab(tauv, b0, vs), tauh_S = last_slab(tauhv, b0, vs);
+        pcache.add(T, true); pcache.add(Tt, true);
+        if (singles) { pcache.add(tau, true); pcache.add(tauh, true); }
 
         // ---- small intermediates: partial sums over f in the slab, one all-reduce -------------------
         const int64_t nFae = v * v, nFmi = o * o, nW = o * o * o * o, nR1 = o * v;
@@ -335,6 +345,7 @@ struct CC {
         const Ten Tn_S = last_slab(T2n, b0, vs);
         residual_finish(ctx, V_S.p, Lpp.p(), Lhh.p(), H.p, Hfull.p(), Tn_S.p, P.eo.p, P.ev.p, o, v, b0, vs);
         all_gather_inplace(ctx, T2n.p(), ns);
+        pcache.end_sweep();
         std::swap(T2.buf, T2n.buf); std::swap(T2.t, T2n.t);
         if (singles) { std::swap(T1.buf, T1n.buf); std::swap(T1.t, T1n.t); }
     }
@@ -365,6 +376,7 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
     JUES_REQUIRE(maxit >= 0, "maxit must be non-negative");
     CC cc(ctx, P, singles);
     cc.build_integrals(gao);
+    cc.register_static();
     cc.guess(guess_mode);
     CCResult res;
     res.e_hist.resize(maxit + 1);

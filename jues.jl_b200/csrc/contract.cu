@@ -46,6 +46,41 @@ std::string pick(const char* from, const std::string& set) {
     return r;
 }
 
+// permuted copy of X (axes `ix`) in axis order `tgt`: from the context's PermCache when X is a
+// registered tensor (and memory allows keeping the copy), otherwise into the temporary `tmp`
+const double* permuted_operand(jues_ctx* ctx, const Ten& X, const char* ix, const std::string& tgt,
+                               const int64_t* tgt_dims, DTen& tmp) {
+    Ten t = X;
+    for (size_t q = 0; q < tgt.size(); ++q) t.d[q] = tgt_dims[q];
+    PermCache* pc = static_cast<PermCache*>(ctx->perm_cache);
+    if (pc) {
+        for (const auto& r : pc->ranges) {
+            if (X.p < r.lo || X.p >= r.hi) continue;
+            char key[160];
+            snprintf(key, sizeof key, "%p:%lld,%lld,%lld,%lld:%s>%s", (const void*)X.p, (long long)X.d[0],
+                     (long long)X.d[1], (long long)X.d[2], (long long)X.d[3], ix, tgt.c_str());
+            for (auto& e : pc->entries)
+                if (e.key == key) return e.buf.p;
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const size_t bytes = (size_t)X.size() * 8;
+            if (free_b + ctx->big_cached_bytes < 4 * bytes + (size_t(8) << 30)) break;  // keep headroom
+            PermCache::Entry e;
+            e.key = key;
+            e.sweep = r.sweep;
+            e.buf.alloc(ctx, (size_t)X.size());
+            t.p = e.buf.p;
+            permute_axpby(ctx, 1.0, X, ix, 0.0, t, tgt.c_str());
+            pc->entries.push_back(std::move(e));
+            return pc->entries.back().buf.p;
+        }
+    }
+    tmp.buf.alloc(ctx, (size_t)X.size());
+    t.p = tmp.buf.p;
+    permute_axpby(ctx, 1.0, X, ix, 0.0, t, tgt.c_str());
+    return tmp.buf.p;
+}
+
 }  // namespace
 
 void contract(jues_ctx* ctx, double alpha, const Ten& A, const char* ia, const Ten& B, const char* ib,
@@ -107,22 +142,18 @@ void contract(jues_ctx* ctx, double alpha, const Ten& A, const char* ia, const T
     else {
         // permute into K-contiguous form [K..., M...]
         const std::string tgt = kord + mord;
-        tmpA.buf.alloc(ctx, (size_t)A.size());
-        Ten t = A; t.p = tmpA.buf.p;
-        for (size_t q = 0; q < tgt.size(); ++q) t.d[q] = extent_of(tgt[q], A, ia, B, ib, C, ic);
-        permute_axpby(ctx, 1.0, A, ia, 0.0, t, tgt.c_str());
-        pa = tmpA.buf.p;
+        int64_t td[4] = {1, 1, 1, 1};
+        for (size_t q = 0; q < tgt.size(); ++q) td[q] = extent_of(tgt[q], A, ia, B, ib, C, ic);
+        pa = permuted_operand(ctx, A, ia, tgt, td, tmpA);
         a_t = true;
     }
     if (is_concat(sb, kord, nord)) b_t = false;       // stored K x N
     else if (is_concat(sb, nord, kord)) b_t = true;   // stored N x K
     else {
         const std::string tgt = kord + nord;
-        tmpB.buf.alloc(ctx, (size_t)B.size());
-        Ten t = B; t.p = tmpB.buf.p;
-        for (size_t q = 0; q < tgt.size(); ++q) t.d[q] = extent_of(tgt[q], A, ia, B, ib, C, ic);
-        permute_axpby(ctx, 1.0, B, ib, 0.0, t, tgt.c_str());
-        pb = tmpB.buf.p;
+        int64_t td[4] = {1, 1, 1, 1};
+        for (size_t q = 0; q < tgt.size(); ++q) td[q] = extent_of(tgt[q], A, ia, B, ib, C, ic);
+        pb = permuted_operand(ctx, B, ib, tgt, td, tmpB);
         b_t = false;
     }
 

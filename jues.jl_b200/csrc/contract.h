@@ -2,7 +2,30 @@
 #pragma once
 #include "tensor_ops.h"
 
+#include <string>
+#include <vector>
+
 namespace jues {
+
+// Memo of permuted operand copies.  contract() permutes an operand whose axis order does not form
+// a matrix; when the operand lies inside a registered allocation the permuted copy is kept:
+// static integrals are permuted once per calculation, amplitude-derived tensors once per sweep.
+struct PermCache {
+    struct Range { const double* lo; const double* hi; bool sweep; };
+    struct Entry { std::string key; DBuf buf; bool sweep; };
+    std::vector<Range> ranges;
+    std::vector<Entry> entries;
+    void add(const Ten& t, bool sweep) { ranges.push_back({t.p, t.p + t.size(), sweep}); }
+    // drop everything derived from per-sweep tensors
+    void end_sweep() {
+        for (size_t k = 0; k < entries.size();)
+            if (entries[k].sweep) { entries[k] = std::move(entries.back()); entries.pop_back(); } else ++k;
+        for (size_t k = 0; k < ranges.size();)
+            if (ranges[k].sweep) { ranges[k] = ranges.back(); ranges.pop_back(); } else ++k;
+    }
+    void clear() { entries.clear(); ranges.clear(); }
+};
+
 // C[ic] = alpha * sum_{shared letters} A[ia] * B[ib] + beta * C[ic]
 void contract(jues_ctx* ctx, double alpha, const Ten& A, const char* ia, const Ten& B, const char* ib,
               double beta, const Ten& C, const char* ic);

@@ -93,6 +93,7 @@ struct jues_ctx {
     int nranks = 1;
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
+    void* perm_cache = nullptr;   // jues::PermCache of the running calculation (contract.h)
     // per-sweep amplitude capture (tests)
     jues_b200_amp_cb amp_cb = nullptr;
     void* amp_user = nullptr;
