@@ -23,6 +23,12 @@ static const Cfg kCfgs[] = {
     {64, 128, 32, 32, 6, "64x128x16_w32x32_s6", 1.12},
     {128, 64, 64, 16, 6, "128x64x16_w64x16_s6", 1.12},
     {64, 64, 32, 16, 8, "64x64x16_w32x16_s8", 1.30},
+    // 1 x 8 warp layouts: 16-row granularity in M against tile / wave quantisation (e.g. M = 400 = 5 x 80,
+    // M = 2000 -> 18 x 112 x 16 tiles = 288 CTAs = 1.95 waves of 148 SMs)
+    {112, 128, 112, 16, 5, "112x128x16_w112x16_s5", 1.03},
+    {96, 128, 96, 16, 5, "96x128x16_w96x16_s5", 1.05},
+    {80, 128, 80, 16, 6, "80x128x16_w80x16_s6", 1.07},
+    {48, 128, 48, 16, 8, "48x128x16_w48x16_s8", 1.20},
 };
 constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 
@@ -34,7 +40,11 @@ KernelFn kernel_for(int cfg, int* smem) {
         case 0: *smem = SmemLayout<128, 128, 4>::TOTAL; return dgemm_tma_dmma<A_KC, B_KC, 128, 128, 64, 32, 4>;
         case 1: *smem = SmemLayout<64, 128, 6>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 64, 128, 32, 32, 6>;
         case 2: *smem = SmemLayout<128, 64, 6>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 128, 64, 64, 16, 6>;
-        default: *smem = SmemLayout<64, 64, 8>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 64, 64, 32, 16, 8>;
+        case 3: *smem = SmemLayout<64, 64, 8>::TOTAL;   return dgemm_tma_dmma<A_KC, B_KC, 64, 64, 32, 16, 8>;
+        case 4: *smem = SmemLayout<112, 128, 5>::TOTAL; return dgemm_tma_dmma<A_KC, B_KC, 112, 128, 112, 16, 5>;
+        case 5: *smem = SmemLayout<96, 128, 5>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 96, 128, 96, 16, 5>;
+        case 6: *smem = SmemLayout<80, 128, 6>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 80, 128, 80, 16, 6>;
+        default: *smem = SmemLayout<48, 128, 8>::TOTAL; return dgemm_tma_dmma<A_KC, B_KC, 48, 128, 48, 16, 8>;
     }
 }
 

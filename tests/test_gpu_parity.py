@@ -38,6 +38,22 @@ def test_gemm(ctx, shape, tA, tB):
     assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("cfg", range(8))
+@pytest.mark.parametrize("split", [1, 3])
+def test_gemm_every_tile_configuration(ctx, cfg, split, monkeypatch):
+    """Force each tile configuration (and split-K) of the DGEMM on ragged shapes, all transposes."""
+    monkeypatch.setenv("JUES_B200_GEMM_CFG", str(cfg + 8 * (split - 1)))
+    rng = np.random.default_rng(cfg)
+    for (M, N, K) in [(131, 257, 100), (400, 300, 77), (30, 17, 200)]:
+        for tA in "NT":
+            for tB in "NT":
+                A = rng.standard_normal((K, M) if tA == "T" else (M, K))
+                B = rng.standard_normal((N, K) if tB == "T" else (K, N))
+                ref = (A.T if tA == "T" else A) @ (B.T if tB == "T" else B)
+                out = ctx.gemm(tA, tB, 1.0, A, B)
+                assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (cfg, split, M, N, K, tA, tB)
+
+
 def test_gemm_skinny_splitk(ctx):
     """o x o output with a very long K (the Fmi / Fae shape) takes the split-K path."""
     rng = np.random.default_rng(5)
