@@ -2,6 +2,7 @@
 // rank-4 tensor handle (include/jues_b200.h).
 #include "api_util.h"
 #include "cc.h"
+#include "dist.h"
 
 #include <memory>
 
@@ -85,7 +86,8 @@ void transform_common(jues_ctx* ctx, GaoSource& src, const double* const Ch[4], 
     int64_t dp[4];
     for (int q = 0; q < 4; ++q) {
         JUES_REQUIRE(Ch[q] != nullptr && d[q] > 0, "null or empty coefficient matrix");
-        dp[q] = round_up(d[q], 2);
+        // multi-GPU: the LAST MO index is split into equal even slabs, one per rank
+        dp[q] = round_up(d[q], q == 3 ? 2 * (int64_t)ctx->nranks : 2);
         upload_padded_matrix(ctx, Cd[q], Ch[q], nao, d[q], np, dp[q]);
         Cm[q] = Cd[q].p;
     }
@@ -93,7 +95,13 @@ void transform_common(jues_ctx* ctx, GaoSource& src, const double* const Ch[4], 
     DBuf chem(ctx, n);
     {
         Timer t(ctx, "tei.transform");
-        tei_transform_dev(ctx, src, Cm, dp, chem.p);
+        int64_t b0, vs;
+        slab_of(ctx, dp[3], &b0, &vs);
+        const double* Cs[4] = {Cm[0], Cm[1], Cm[2], Cm[3] + b0 * np};
+        const int64_t ds[4] = {dp[0], dp[1], dp[2], vs};
+        const size_t per_rank = (size_t)(dp[0] * dp[1] * dp[2] * vs);
+        tei_transform_dev(ctx, src, Cs, ds, chem.p + (size_t)ctx->rank * per_rank);
+        all_gather_inplace(ctx, chem.p, per_rank);   // every rank ends with the whole tensor
     }
     if (phys_order) {
         Timer t(ctx, "tei.permute");
@@ -158,8 +166,7 @@ extern "C" int jues_b200_tei_transform_t4(jues_ctx* ctx, const jues_t4* gao, con
     jues_t4* t = nullptr;
     int rc = jues_b200_t4_create(ctx, dl[0], dl[1], dl[2], dl[3], &t);
     if (rc) return rc;
-    JUES_CUDA(cudaMemcpyAsync(t->p, res.p, (size_t)(dp[0] * dp[1] * dp[2] * dp[3]) * 8,
-                              cudaMemcpyDeviceToDevice, ctx->stream));
+    block_copy(ctx, res.p, dp, t->p, t->dp, dl);   // padded extents may differ (multi-GPU slab padding)
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = t;
     JUES_API_END(ctx)

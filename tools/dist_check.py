@@ -21,6 +21,9 @@ def main():
         e_sd, T1, T2 = jb.RCCSD.do_rccsd(w, ctx=ctx, _return_T=True, _e_hist=h1)
         e_d, T2d = jb.RCCD.do_rccd(w, ctx=ctx, _return_T2=True, _e_hist=h2)
         e_mp2 = jb.do_rmp2(w, ctx=ctx)
+        # sharded stand-alone transform (last MO index split over ranks, all-gathered)
+        tei = jb.tei_transform(g, Cao, Cav, Cav, np.hstack([Cao, Cav]), "x", ctx=ctx)
+        tei_p = jb.get_eri(w, "OVOV", ctx=ctx)
         # identical on every rank
         t = torch.tensor([e_sd, e_d, e_mp2, float(np.abs(T2).sum()), float(np.abs(T1).sum())], dtype=torch.float64, device="cuda")
         lo, hi = t.clone(), t.clone()
@@ -37,6 +40,9 @@ def main():
             edr, T2dr = orc.do_rccd(wo, return_T2=True, callback=lambda it, e, b: refd.append(e))
             errs += [abs(e_d - edr), np.abs(np.array(h2) - np.array(refd)).max(), np.abs(T2d - T2dr).max(),
                      abs(e_mp2 - orc.do_rmp2(wo))]
+            terr = max(np.abs(tei - orc.tei_transform(g, Cao, Cav, Cav, np.hstack([Cao, Cav]))).max(),
+                       np.abs(tei_p - orc.get_eri(wo, "OVOV")).max()) / np.abs(g).max()
+            assert terr < 1e-12, terr
             print(f"N={N} o={o} world={world} errs={['%.1e' % x for x in errs]} comm={ctx.comm_counters()}", flush=True)
             worst = max(worst, max(errs[0], errs[1], errs[4], errs[5], errs[7]) / 1e-10, max(errs[2], errs[3], errs[6]) / 1e-9)
     ok = torch.tensor([1.0 if worst <= 1.0 else 0.0], device="cuda")
