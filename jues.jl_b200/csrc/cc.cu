@@ -334,11 +334,14 @@ struct CC {
             DTen Yp(ctx, o, o, o, vs);
             contract(ctx, 1.0, tauv, "ijef", OA, "efmb", 0.0, Yp, "ijmb");
             contract(ctx, -1.0, Yp, "ijmb", t, "ma", 1.0, H, "ijab");
-            DTen Z(ctx, v, o, v, vs);
-            contract(ctx, 1.0, t, "ma", V_S, "mjeb", 0.0, Z, "ajeb");
-            contract(ctx, 1.0, tS, "mb", J, "maje", 1.0, Z, "ajeb");
-            contract(ctx, 1.0, t, "ie", OB, "ajeb", 1.0, H, "ijab");
-            contract(ctx, -1.0, t, "ie", Z, "ajeb", 1.0, H, "ijab");
+            // rank-1 ring corrections  - t[ie] t[ma] <mb|ej>  - t[ie] t[mb] <am|ej>: contract t[ie] into the
+            // integral first (o^3 v intermediates) instead of building v^3 o ones
+            DTen Q1(ctx, o, o, o, vs), Q2(ctx, o, o, v, o);
+            contract(ctx, 1.0, t, "ie", V_S, "mjeb", 0.0, Q1, "imjb");
+            contract(ctx, -1.0, Q1, "imjb", t, "ma", 1.0, H, "ijab");
+            contract(ctx, 1.0, t, "ie", J, "maje", 0.0, Q2, "imaj");
+            contract(ctx, -1.0, Q2, "imaj", tS, "mb", 1.0, H, "ijab");
+            contract(ctx, 1.0, t, "ie", OB, "ajeb", 1.0, H, "ijab");     // t . <ab|ej>
             contract(ctx, -1.0, t, "ma", last_slab(ooov, b0, vs), "mjib", 1.0, H, "ijab");
         }
         all_gather_inplace(ctx, Hfull.p(), ns);

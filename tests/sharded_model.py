@@ -119,8 +119,11 @@ def sweep(R, t, T, eo, ev, b0, b1, comm=None, singles=True):
     if singles:
         Yp = es("ijef,efmb->ijmb", tau, OA)
         H -= es("ijmb,ma->ijab", Yp, t)
-        Z = es("ma,mjeb->ajeb", t, V[..., S]) + es("mb,maje->ajeb", tS, J)
-        H += es("ie,ajeb->ijab", t, OB - Z)
+        Q1 = es("ie,mjeb->imjb", t, V[..., S])
+        H -= es("imjb,ma->ijab", Q1, t)
+        Q2 = es("ie,maje->imaj", t, J)
+        H -= es("imaj,mb->ijab", Q2, tS)
+        H += es("ie,ajeb->ijab", t, OB)
         H -= es("ma,mjib->ijab", t, ooov[..., S])
     Hfull = comm.allgather_last(H)
     PH = Hfull.transpose(1, 0, 3, 2)[..., S]
