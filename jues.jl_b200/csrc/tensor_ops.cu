@@ -60,18 +60,38 @@ struct PermArgs {
     double alpha, beta;
 };
 
-// output-fastest axis is also input-fastest (sin[0] == 1): straight coalesced copy
+// output-fastest axis is also input-fastest (sin[0] == 1): rows of n[0] contiguous elements are
+// copied as they are; one warp per row (index arithmetic once per row, not per element), lanes
+// stride along the row with 4 independent loads in flight each
 __global__ void permute_same_fast(const double* __restrict__ in, double* __restrict__ out, PermArgs a) {
-    long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; L < a.total; L += stride) {
-        long long r = L;
-        const long long i0 = r % a.n[0]; r /= a.n[0];
+    const long long rows = a.n[1] * a.n[2] * a.n[3];
+    const int lane = threadIdx.x & 31;
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long rstride = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long n0 = a.n[0];
+    for (; row < rows; row += rstride) {
+        long long r = row;
         const long long i1 = r % a.n[1]; r /= a.n[1];
-        const long long i2 = r % a.n[2]; r /= a.n[2];
-        const long long i3 = r;
-        const double v = a.alpha * in[i0 * a.sin[0] + i1 * a.sin[1] + i2 * a.sin[2] + i3 * a.sin[3]];
-        out[L] = (a.beta == 0.0) ? v : v + a.beta * out[L];
+        const long long i2 = r % a.n[2];
+        const long long i3 = r / a.n[2];
+        const double* __restrict__ src = in + i1 * a.sin[1] + i2 * a.sin[2] + i3 * a.sin[3];
+        double* __restrict__ dst = out + row * n0;
+        long long i = lane;
+        for (; i + 96 < n0; i += 128) {
+            const double v0 = src[i], v1 = src[i + 32], v2 = src[i + 64], v3 = src[i + 96];
+            if (a.beta == 0.0) {
+                dst[i] = a.alpha * v0; dst[i + 32] = a.alpha * v1; dst[i + 64] = a.alpha * v2; dst[i + 96] = a.alpha * v3;
+            } else {
+                dst[i] = a.alpha * v0 + a.beta * dst[i];
+                dst[i + 32] = a.alpha * v1 + a.beta * dst[i + 32];
+                dst[i + 64] = a.alpha * v2 + a.beta * dst[i + 64];
+                dst[i + 96] = a.alpha * v3 + a.beta * dst[i + 96];
+            }
+        }
+        for (; i < n0; i += 32) {
+            const double v = a.alpha * src[i];
+            dst[i] = (a.beta == 0.0) ? v : v + a.beta * dst[i];
+        }
     }
 }
 
@@ -404,7 +424,14 @@ void permute_axpby(jues_ctx* ctx, double alpha, const Ten& in, const char* ii, d
         PermArgs a;
         for (int q = 0; q < 4; ++q) { a.n[q] = n[q]; a.sin[q] = sin[q]; }
         a.total = total; a.alpha = alpha; a.beta = beta;
-        permute_same_fast<<<ew_grid(ctx, (size_t)total, 256), 256, 0, ctx->stream>>>(in.p, out.p, a);
+        {
+            const long long rows = a.n[1] * a.n[2] * a.n[3];
+            long long blocks = (rows + 7) / 8;   // 8 warps (rows) per block
+            const long long capb = (long long)ctx->sm_count * 32;
+            if (blocks > capb) blocks = capb;
+            if (blocks < 1) blocks = 1;
+            permute_same_fast<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in.p, out.p, a);
+        }
         AUX_LAUNCHED(ctx);
         return;
     }
@@ -459,7 +486,7 @@ void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const dou
     }
     long long blocks = (long long)v * vs;
     if (blocks == 0) return;
-    const long long cap = (long long)ctx->sm_count * 8;
+    const long long cap = (long long)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
     residual_finish_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(V, L1, L2, H, Hfull, Tnew, eo, ev,
                                                                          (int)o, (int)v, (int)b0, (int)vs);
@@ -483,7 +510,7 @@ static double finish_reduction(jues_ctx* ctx, int nblocks) {
 
 static int reduction_blocks(jues_ctx* ctx, int64_t v) {
     long long blocks = (long long)v * v;
-    const long long cap = (long long)ctx->sm_count * 4;
+    const long long cap = (long long)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
     if (blocks > (long long)ctx->red_cap - 2) blocks = (long long)ctx->red_cap - 2;
     return (int)blocks;
@@ -499,7 +526,7 @@ double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* 
 double mp2_energy(jues_ctx* ctx, const double* V, const double* eo, const double* ev, int64_t o, int64_t v,
                   int64_t b0, int64_t vs) {
     long long blocks = (long long)v * vs;
-    const long long cap = std::min<long long>((long long)ctx->sm_count * 4, (long long)ctx->red_cap - 4);
+    const long long cap = std::min<long long>((long long)ctx->sm_count * 16, (long long)ctx->red_cap - 4);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     mp2_energy_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(V, eo, ev, (int)o, (int)v, (int)b0, (int)vs,
