@@ -375,6 +375,12 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner on fd 1) are
+    # diverted to stderr for the duration of the run; the line is written to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         reference_arm(args, rank)
         return

@@ -258,6 +258,7 @@ struct CC {
         if (singles) { pcache.add(tau, true); pcache.add(tauh, true); }
 
         // ---- small intermediates: partial sums over f in the slab, one all-reduce -------------------
+        TraceTimer* tr_small = new TraceTimer(ctx, "cc.part.small");
         const int64_t nFae = v * v, nFmi = o * o, nW = o * o * o * o, nR1 = o * v;
         DBuf small(ctx, (size_t)(nFae + nFmi + nW + nR1));
         Ten FaeT(small.p, v, v), Fmi(small.p + nFae, o, o), Wpp(small.p + nFae + nFmi, o, o, o, o),
@@ -274,7 +275,8 @@ struct CC {
         } else {
             fill(ctx, R1.p, (size_t)nR1, 0.0);
         }
-        all_reduce_sum(ctx, small.p, small.n);
+        delete tr_small;
+        { TraceTimer tt(ctx, "cc.comm.allreduce"); all_reduce_sum(ctx, small.p, small.n); }
         axpby(ctx, (size_t)nW, 1.0, oooo.p(), 1.0, Wpp.p);
         DTen Fme, FaeT_t, Fmi_t;
         Ten FaeTt = FaeT, FmiT = Fmi;
@@ -299,6 +301,7 @@ struct CC {
             FaeTt = FaeT_t; FmiT = Fmi_t;
         }
         // ---- ring intermediates for the slab, layout [m,e,j,b] ------------------------------------
+        TraceTimer* tr_ring = new TraceTimer(ctx, "cc.part.ringW");
         const size_t ns = (size_t)(o * o * v * vs);
         DTen WJ(ctx, o, v, o, vs), WE(ctx, o, v, o, vs);
         permute_axpby(ctx, 1.0, V_S, "mjeb", 0.0, WJ, "mejb");                       // <mb|ej> = <mj|eb>
@@ -319,7 +322,9 @@ struct CC {
             contract(ctx, -0.5, V, "mnef", T_S, "jnfb", 1.0, WJ, "mejb");
             contract(ctx, 0.5, V, "nmef", T_S, "jnfb", 1.0, WE, "mejb");
         }
+        delete tr_ring;
         // ---- ladders ---------------------------------------------------------------------------------
+        TraceTimer* tr_lad = new TraceTimer(ctx, "cc.part.ladders+H");
         DTen Lpp(ctx, o, o, v, vs), Lhh(ctx, o, o, v, vs), Hfull(ctx, o, o, v, v);
         const Ten H = last_slab(Hfull, b0, vs);
         contract(ctx, 1.0, tauv, "ijef", W4, "efab", 0.0, Lpp, "ijab");
@@ -344,10 +349,11 @@ struct CC {
             contract(ctx, 1.0, t, "ie", OB, "ajeb", 1.0, H, "ijab");     // t . <ab|ej>
             contract(ctx, -1.0, t, "ma", last_slab(ooov, b0, vs), "mjib", 1.0, H, "ijab");
         }
-        all_gather_inplace(ctx, Hfull.p(), ns);
+        delete tr_lad;
+        { TraceTimer tt(ctx, "cc.comm.gatherH"); all_gather_inplace(ctx, Hfull.p(), ns); }
         const Ten Tn_S = last_slab(T2n, b0, vs);
         residual_finish(ctx, V_S.p, Lpp.p(), Lhh.p(), H.p, Hfull.p(), Tn_S.p, P.eo.p, P.ev.p, o, v, b0, vs);
-        all_gather_inplace(ctx, T2n.p(), ns);
+        { TraceTimer tt(ctx, "cc.comm.gatherT2"); all_gather_inplace(ctx, T2n.p(), ns); }
         pcache.end_sweep();
         std::swap(T2.buf, T2n.buf); std::swap(T2.t, T2n.t);
         if (singles) { std::swap(T1.buf, T1n.buf); std::swap(T1.t, T1n.t); }

@@ -240,4 +240,14 @@ struct Timer {
     }
 };
 
+// JUES_B200_TRACE=1: fine-grained CUDA-event timings (each one synchronises the stream)
+struct TraceTimer {
+    Timer* t = nullptr;
+    TraceTimer(jues_ctx* ctx, const char* name) {
+        static const bool on = getenv("JUES_B200_TRACE") != nullptr;
+        if (on) t = new Timer(ctx, name);
+    }
+    ~TraceTimer() { delete t; }
+};
+
 }  // namespace jues

@@ -65,16 +65,6 @@ void upload_padded_gao(jues_ctx* ctx, double* dst, const double* host, int64_t n
 
 namespace {
 
-// JUES_B200_TRACE=1: per-stage CUDA-event timings of the transform (serialises the stream)
-struct TraceTimer {
-    Timer* t = nullptr;
-    TraceTimer(jues_ctx* ctx, const char* name) {
-        static const bool on = getenv("JUES_B200_TRACE") != nullptr;
-        if (on) t = new Timer(ctx, name);
-    }
-    ~TraceTimer() { delete t; }
-};
-
 double quarter_flops(const int64_t e[4], int axis, int64_t d) {
     return 2.0 * (double)e[0] * (double)e[1] * (double)e[2] * (double)e[3] * (double)d;
 }
