@@ -72,23 +72,57 @@ def make_inputs(pinned: bool):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    NVML is queried in-process (two cheap calls every 20 ms).  An `nvidia-smi -lms 100` loop with
+    the usual field list was measured to stall the GPUs for tens of milliseconds at a time (sweeps
+    of 9.8 ms jittered up to 90 ms with it, on 2 GPUs), so it is only the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device):
         self.device = device
-        self.rows = []
+        self.sm = []
+        self.bits = 0
+        self.max_mhz = None
+        self.stop_flag = False
+        self.thread = None
         self.proc = None
+        self.rows = []
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):
+            return
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.device]) if vis and vis.split(",")[0].isdigit() else self.device
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.02)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
@@ -97,8 +131,16 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            # under load = samples within 25 % of the maximum observed during the run
+            busy = [x for x in self.sm if x >= 0.75 * max(self.sm)] if self.sm else []
+            return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b),
+                    "samples": len(self.sm), "how": "NVML in-process, 20 ms period"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -115,7 +157,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": "nvidia-smi -lms 500"}
 
 
 def fp64_peak():
@@ -356,6 +398,7 @@ def gpu_arm(args, rank, world):
                 "s_per_do_rccsd": t_call, "s_per_iteration": t_call / REF_MAXIT,
                 "what": "jues_b200_rccsd(host gao, Cao, Cav, eps, maxit=40): H2D + transform + 40 sweeps + energies D2H"},
         "gpu_launches": int(round(launches_step)),
+        "ms_each_step_rank0": [round(x, 3) for x in it_ms],
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,
