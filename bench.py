@@ -74,7 +74,7 @@ def make_inputs(pinned: bool):
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region.
 
-    NVML is queried in-process (two cheap calls every 20 ms).  An `nvidia-smi -lms 100` loop with
+    NVML is queried in-process (two cheap calls every 100 ms).  An `nvidia-smi -lms 100` loop with
     the usual field list was measured to stall the GPUs for tens of milliseconds at a time (sweeps
     of 9.8 ms jittered up to 90 ms with it, on 2 GPUs), so it is only the fallback."""
 
@@ -108,7 +108,7 @@ class ClockSampler:
                         self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                     except Exception:
                         pass
-                    time.sleep(0.02)
+                    time.sleep(0.1)
 
             self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
@@ -138,7 +138,7 @@ class ClockSampler:
             busy = [x for x in self.sm if x >= 0.75 * max(self.sm)] if self.sm else []
             return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": self.max_mhz,
                     "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b),
-                    "samples": len(self.sm), "how": "NVML in-process, 20 ms period"}
+                    "samples": len(self.sm), "how": "NVML in-process, 100 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         self.proc.terminate()
