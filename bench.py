@@ -86,6 +86,7 @@ class ClockSampler:
         self.bits = 0
         self.max_mhz = None
         self.stop_flag = False
+        self.period = float(os.environ.get("BENCH_SAMPLER_PERIOD", "0.1"))
         self.thread = None
         self.proc = None
         self.rows = []
@@ -101,14 +102,21 @@ class ClockSampler:
             h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
+            self.t_clock = self.t_reason = 0.0
+
             def loop():
                 while not self.stop_flag:
                     try:
+                        t0 = time.perf_counter()
                         self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        t1 = time.perf_counter()
                         self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        t2 = time.perf_counter()
+                        self.t_clock = max(self.t_clock, t1 - t0)
+                        self.t_reason = max(self.t_reason, t2 - t1)
                     except Exception:
                         pass
-                    time.sleep(0.1)
+                    time.sleep(self.period)
 
             self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
@@ -138,7 +146,8 @@ class ClockSampler:
             busy = [x for x in self.sm if x >= 0.75 * max(self.sm)] if self.sm else []
             return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": self.max_mhz,
                     "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b),
-                    "samples": len(self.sm), "how": "NVML in-process, 100 ms period"}
+                    "samples": len(self.sm), "how": f"NVML in-process, {self.period * 1e3:.0f} ms period",
+                    "nvml_call_max_ms": [round(self.t_clock * 1e3, 3), round(self.t_reason * 1e3, 3)]}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
         self.proc.terminate()
@@ -284,6 +293,8 @@ def gpu_arm(args, rank, world):
 
     # ---- value: K timed sweeps after W warm-up sweeps, device-resident inputs --------------
     sampler = ClockSampler(local)
+    if rank != 0:
+        os.environ["BENCH_NO_SAMPLER"] = "1"      # one sampler per job: NVML queries perturb the GPUs
     barrier()
     sampler.start()
     hist = []
