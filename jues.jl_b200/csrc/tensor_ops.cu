@@ -302,18 +302,19 @@ __global__ void final_reduce_kernel(const double* __restrict__ partial, int n, d
     if (threadIdx.x == 0) out[0] = r;
 }
 
-__global__ void synth_eri_kernel(double* __restrict__ g, long long n, long long np, long long sig_lo,
-                                 long long sig_count, unsigned long long seed, double scale, int phys) {
-    const long long total = np * np * np * sig_count;
+__global__ void synth_eri_kernel(double* __restrict__ g, long long n, long long np, long long lam_lo,
+                                 long long lam_count, long long sig_lo, long long sig_count,
+                                 unsigned long long seed, double scale, int phys) {
+    const long long total = np * np * lam_count * sig_count;
     long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; L < total; L += stride) {
         long long r = L;
         const unsigned long long mu = r % np; r /= np;
         unsigned long long nu = r % np; r /= np;
-        unsigned long long lam = r % np;
+        unsigned long long lam = (unsigned long long)(r % lam_count) + lam_lo;
         if (phys) { const unsigned long long tmp = nu; nu = lam; lam = tmp; }  // g'[mu,lam,nu,sig]
-        const unsigned long long sig = (unsigned long long)(r / np) + sig_lo;
+        const unsigned long long sig = (unsigned long long)(r / lam_count) + sig_lo;
         double val = 0.0;
         if (mu < (unsigned long long)n && nu < (unsigned long long)n && lam < (unsigned long long)n &&
             sig < (unsigned long long)n) {
@@ -547,9 +548,16 @@ void block_copy(jues_ctx* ctx, const double* src, const int64_t sd[4], double* d
 
 void synth_eri_fill(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t sig_lo,
                     int64_t sig_count, unsigned long long seed, double scale, bool phys) {
-    const size_t total = (size_t)n_padded * n_padded * n_padded * sig_count;
-    synth_eri_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(g, n_logical, n_padded, sig_lo,
-                                                                        sig_count, seed, scale, phys ? 1 : 0);
+    synth_eri_block(ctx, g, n_logical, n_padded, 0, n_padded, sig_lo, sig_count, seed, scale, phys);
+}
+
+void synth_eri_block(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t lam_lo,
+                     int64_t lam_cnt, int64_t sig_lo, int64_t sig_cnt, unsigned long long seed, double scale,
+                     bool phys) {
+    const size_t total = (size_t)n_padded * n_padded * lam_cnt * sig_cnt;
+    if (!total) return;
+    synth_eri_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(g, n_logical, n_padded, lam_lo, lam_cnt,
+                                                                        sig_lo, sig_cnt, seed, scale, phys ? 1 : 0);
     AUX_LAUNCHED(ctx);
 }
 

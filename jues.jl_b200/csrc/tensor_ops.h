@@ -84,6 +84,11 @@ double mp2_energy(jues_ctx* ctx, const double* v, const double* eo, const double
 void synth_eri_fill(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t sig_lo,
                     int64_t sig_count, unsigned long long seed, double scale, bool phys = false);
 
+// general block g[:, :, l0:l0+lc, s0:s0+sc] of the same generator, dense (np, np, lc, sc)
+void synth_eri_block(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t lam_lo,
+                     int64_t lam_cnt, int64_t sig_lo, int64_t sig_cnt, unsigned long long seed, double scale,
+                     bool phys);
+
 }  // namespace jues
 
 namespace jues {

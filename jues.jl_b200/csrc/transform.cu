@@ -19,6 +19,13 @@ const double* SynthGao::slab(jues_ctx* ctx, int64_t lo, int64_t cnt) {
     return stage.p;
 }
 
+const double* SynthGao::block3(jues_ctx* ctx, int64_t lo, int64_t cnt) {
+    const int64_t need = np * np * cnt * np;
+    if ((int64_t)stage.n < need) stage.alloc(ctx, (size_t)need);
+    synth_eri_block(ctx, stage.p, n, np, lo, cnt, 0, np, seed, scale, phys);
+    return stage.p;
+}
+
 void upload_padded_matrix(jues_ctx* ctx, DBuf& dst, const double* host, int64_t n, int64_t d, int64_t np,
                           int64_t dp) {
     dst.alloc(ctx, (size_t)(np * dp));
@@ -166,6 +173,25 @@ void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4],
             cnt &= ~int64_t(1);
             const int64_t s_begin = gao.sig_lo, s_end = gao.sig_hi < 0 ? np : gao.sig_hi;
             if (s_begin >= s_end) JUES_CUDA(cudaMemsetAsync(dst, 0, nout * sizeof(double), ctx->stream));
+            if (gao.has_block3() && s_begin < s_end) {
+                // blocks of the third index: out[(mu,nu,lam in block), b] = g[(mu,nu,lam), sigma] C4[sigma, b]
+                // with the whole sigma range as K -- disjoint row blocks of the output, no accumulation
+                for (int64_t lo = 0; lo < np; lo += cnt) {
+                    const int64_t c = std::min(cnt, np - lo);
+                    const double* blk;
+                    {
+                        TraceTimer tt(ctx, "tei.slab");
+                        blk = gao.block3(ctx, lo, c);
+                    }
+                    TraceTimer tq(ctx, "tei.q1");
+                    GemmCall g;
+                    g.M = np * np * c; g.N = dp[3]; g.K = s_end - s_begin;
+                    g.A = blk + s_begin * (np * np * c); g.lda = np * np * c;
+                    g.B = Cm[3] + s_begin; g.ldb = np;
+                    g.C = dst + lo * np * np; g.ldc = plane;
+                    dgemm(ctx, g);
+                }
+            } else
             for (int64_t lo = s_begin; lo < s_end; lo += cnt) {
                 const int64_t c = std::min(cnt, s_end - lo);
                 const double* sl;

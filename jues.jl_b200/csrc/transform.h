@@ -18,6 +18,11 @@ struct GaoSource {
     virtual bool resident() const = 0;          // whole tensor addressable on the device
     virtual const double* base() const { return nullptr; }
     virtual const double* slab(jues_ctx* ctx, int64_t lo, int64_t cnt) = 0;
+    // Optional: a block of the THIRD index, gao[:, :, lo:lo+cnt, :] as a dense (np, np, cnt, np) array.
+    // With it the first quarter contracts the complete sigma range in one GEMM per block (K = N, no
+    // read-modify-write of the N^3 x d4 accumulator per sigma slab).
+    virtual bool has_block3() const { return false; }
+    virtual const double* block3(jues_ctx*, int64_t, int64_t) { return nullptr; }
 };
 
 // dense device tensor (np^4)
@@ -47,6 +52,8 @@ struct SynthGao : GaoSource {
     SynthGao(int64_t n_, int64_t np_, unsigned long long s, double sc) : seed(s), scale(sc) { n = n_; np = np_; }
     bool resident() const override { return false; }
     const double* slab(jues_ctx* ctx, int64_t lo, int64_t cnt) override;
+    bool has_block3() const override { return true; }
+    const double* block3(jues_ctx* ctx, int64_t lo, int64_t cnt) override;
 };
 
 // Upload host matrix C (n x d, column-major, ld = n) into a zero-padded device matrix (np x dp).
