@@ -49,31 +49,44 @@ double rmp2_dev(jues_ctx* ctx, Problem& P, GaoSource& gao) {
     int64_t b0, vs;
     slab_of(ctx, v, &b0, &vs);   // this rank's slab of the virtual index b (everything when nranks == 1)
     // E = sum_{ij a b} v_ijab (2 v_ijab - v_ijba) / D with v_ijba = v_jiab: every (a, b in slab) block is
-    // self-contained, so ranks need no exchange but the final scalar.
-    // A streamed AO tensor is contracted over sigma first and its first-quarter accumulator is
-    // N^3 x (last slot): put the slab last when it is the smaller extent ((ia|j b_S): the first
-    // quarter is then sharded too), the occupied index otherwise ((ia|b_S j)).
-    const bool slab_last = gao.resident() || vs <= o;
-    DTen t4, ijab(ctx, o, o, v, vs);
+    // self-contained, so the energy needs no exchange but the final scalar.
+    DTen ijab;
+    if (gao.resident()) {
+        // resident AO tensor: transform only this rank's slab, (ia|j b_S)
+        DTen t4(ctx, o, v, o, vs);
+        {
+            Timer t(ctx, "mp2.transform");
+            const double* Cm[4] = {P.Co.p, P.Cv.p, P.Co.p, P.Cv.p + b0 * gao.np};
+            const int64_t dp[4] = {o, v, o, vs};
+            tei_transform_dev(ctx, gao, Cm, dp, t4.p());
+        }
+        Timer t(ctx, "mp2.energy");
+        ijab.alloc(ctx, o, o, v, vs);
+        permute_axpby(ctx, 1.0, t4, "iajb", 0.0, ijab, "ijab");   // <ij|ab> (IntegralTransformation.jl:96-98)
+        return all_reduce_scalar(ctx, mp2_energy(ctx, ijab.p(), P.eo.p, P.ev.p, o, v, b0, vs));
+    }
+    // streamed AO tensor: contracted over sigma first with the occupied index in the last slot
+    // ((ia|jb) = (ia|bj): an N^3 x o accumulator instead of N^3 x v).  The transform is linear in
+    // gao, so each rank streams only its share of the sigma range -- generation and the dominant
+    // first quarter are divided by the number of ranks -- and the partial (ia|bj) tensors are summed.
+    DTen t4(ctx, o, v, v, o);
     {
         Timer t(ctx, "mp2.transform");
-        const double* CvS = P.Cv.p + b0 * gao.np;
-        if (slab_last) {
-            const double* Cm[4] = {P.Co.p, P.Cv.p, P.Co.p, CvS};
-            const int64_t dp[4] = {o, v, o, vs};
-            t4.alloc(ctx, o, v, o, vs);
-            tei_transform_dev(ctx, gao, Cm, dp, t4.p());   // (ia|jb), chemists' order
-        } else {
-            const double* Cm[4] = {P.Co.p, P.Cv.p, CvS, P.Co.p};
-            const int64_t dp[4] = {o, v, vs, o};
-            t4.alloc(ctx, o, v, vs, o);
-            tei_transform_dev(ctx, gao, Cm, dp, t4.p());   // (ia|bj) = (ia|jb)
+        if (ctx->nranks > 1) {
+            const int64_t per = round_up((gao.np + ctx->nranks - 1) / ctx->nranks, 2);
+            gao.sig_lo = std::min<int64_t>(gao.np, per * ctx->rank);
+            gao.sig_hi = std::min<int64_t>(gao.np, per * (ctx->rank + 1));
         }
+        const double* Cm[4] = {P.Co.p, P.Cv.p, P.Cv.p, P.Co.p};
+        const int64_t dp[4] = {o, v, v, o};
+        tei_transform_dev(ctx, gao, Cm, dp, t4.p());
+        gao.sig_lo = 0; gao.sig_hi = -1;
+        all_reduce_sum(ctx, t4.p(), (size_t)t4.t.size());
     }
     Timer t(ctx, "mp2.energy");
-    // <ij|ab> (IntegralTransformation.jl:96-98)
-    permute_axpby(ctx, 1.0, t4, slab_last ? "iajb" : "iabj", 0.0, ijab, "ijab");
-    double e = mp2_energy(ctx, ijab.p(), P.eo.p, P.ev.p, o, v, b0, vs);
+    ijab.alloc(ctx, o, o, v, v);
+    permute_axpby(ctx, 1.0, t4, "iabj", 0.0, ijab, "ijab");
+    const double e = mp2_energy(ctx, ijab.p() + b0 * o * o * v, P.eo.p, P.ev.p, o, v, b0, vs);
     return all_reduce_scalar(ctx, e);
 }
 

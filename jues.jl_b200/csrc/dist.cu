@@ -127,6 +127,12 @@ extern "C" int jues_b200_init_dist(jues_ctx* ctx, int rank, int nranks, const un
         ncclComm_t comm;
         nccl_check(g_nccl.CommInitRank(&comm, nranks, uid, rank), "ncclCommInitRank");
         ctx->nccl_comm = comm;
+        // first collective sets up the NVLink connections (seconds): do it here, not inside a timed call
+        double* slot = ctx->red_dev + ctx->red_cap - 2;
+        JUES_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), ctx->stream));
+        all_reduce_sum(ctx, slot, 1);
+        all_gather_inplace(ctx, ctx->red_dev, 1);
+        JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     JUES_API_END(ctx)
 }
