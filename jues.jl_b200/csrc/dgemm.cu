@@ -109,6 +109,11 @@ void choose_cfg(jues_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t batch, b
     *split_out = best_split;
 }
 
+bool persistent_gemm() {
+    static const bool off = getenv("JUES_B200_GEMM_NONPERSISTENT") != nullptr;   // A/B switch for measurements
+    return !off;
+}
+
 }  // namespace
 
 int dgemm_num_configs() { return kNumCfgs; }
@@ -176,7 +181,11 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
         attr_set[(void*)fn] = true;
     }
     const int threads = (c.BM / c.WM) * (c.BN / c.WN) * 32 + 32;
-    fn<<<(unsigned)total, threads, smem, ctx->stream>>>(mapA, mapB, p);
+    p.total_tiles = total;
+    // persistent CTAs (one per SM) once there is more than ~a wave of tiles; otherwise one CTA per tile
+    const long long sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    const long long grid = persistent_gemm() ? std::min<long long>(total, sms) : total;
+    fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(mapA, mapB, p);
     JUES_CUDA(cudaGetLastError());
     ctx->stats.gemm_flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch;
     ctx->stats.gemm_launches += 1;

@@ -32,6 +32,7 @@ struct Params {
     int M, N, K;
     int tilesM, tilesN;
     long long tiles_per_batch;
+    long long total_tiles;   // tiles_per_batch * batch * ksplit; CTAs loop over them (persistent)
     int batch;
     int ksplit;         // split-K factor (1 = off); split z handles k-stages [z*kt_per_split, ...)
     int kt_per_split;
@@ -148,25 +149,10 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // ---- tile coordinates -------------------------------------------------------------------
-    const long long tile = blockIdx.x;
-    const long long bzs = tile / p.tiles_per_batch;  // batch * ksplit + split
-    const int rt = (int)(tile - bzs * p.tiles_per_batch);
-    const int bz = (int)(bzs / p.ksplit);
-    const int zs = (int)(bzs - (long long)bz * p.ksplit);
-    int tm, tn;
-    if (p.raster_n_fast) {
-        tm = rt / p.tilesN;
-        tn = rt - tm * p.tilesN;
-    } else {
-        tn = rt / p.tilesM;
-        tm = rt - tn * p.tilesM;
-    }
-    const int m0 = tm * BM;
-    const int n0 = tn * BN;
+    // Persistent CTAs: CTA b works on tiles b, b + gridDim.x, ...  The TMA producer runs ahead across
+    // tile boundaries (one continuous stage ring), so the loads of the next tile are in flight while the
+    // consumers store the current one: no per-tile launch, barrier-init or first-load latency.
     const int KT_all = (p.K + BK - 1) / BK;
-    const int kt_begin = zs * p.kt_per_split;
-    const int KT = min(KT_all - kt_begin, p.kt_per_split);  // stages this CTA runs (may be <= 0)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -182,28 +168,41 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (uint32_t)((kt / STAGES) & 1);
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                const uint32_t full = bar_full + 8 * s;
-                mbar_expect_tx(full, (uint32_t)L::STAGE_BYTES);
-                const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-                const uint32_t sb = sa + L::A_BYTES;
-                const int k0 = (kt_begin + kt) * BK;
-                if (A_KC) {
-                    tma_load_3d(sa, &mapA, full, k0, m0, bz * p.bmulA);
-                } else {
+            unsigned it = 0;  // stage counter over all tiles of this CTA
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const long long bzs = tile / p.tiles_per_batch;  // batch * ksplit + split
+                const int rt = (int)(tile - bzs * p.tiles_per_batch);
+                const int bz = (int)(bzs / p.ksplit);
+                const int zs = (int)(bzs - (long long)bz * p.ksplit);
+                int tm, tn;
+                if (p.raster_n_fast) { tm = rt / p.tilesN; tn = rt - tm * p.tilesN; }
+                else { tn = rt / p.tilesM; tm = rt - tn * p.tilesM; }
+                const int m0 = tm * BM, n0 = tn * BN;
+                const int kt_begin = zs * p.kt_per_split;
+                const int KT = min(KT_all - kt_begin, p.kt_per_split);
+                for (int kt = 0; kt < KT; ++kt, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    const uint32_t full = bar_full + 8 * s;
+                    mbar_expect_tx(full, (uint32_t)L::STAGE_BYTES);
+                    const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+                    const uint32_t sb = sa + L::A_BYTES;
+                    const int k0 = (kt_begin + kt) * BK;
+                    if (A_KC) {
+                        tma_load_3d(sa, &mapA, full, k0, m0, bz * p.bmulA);
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < BM / 16; ++q)
-                        tma_load_3d(sa + q * 2048, &mapA, full, m0 + 16 * q, k0, bz * p.bmulA);
-                }
-                if (B_KC) {
-                    tma_load_3d(sb, &mapB, full, k0, n0, bz * p.bmulB);
-                } else {
+                        for (int q = 0; q < BM / 16; ++q)
+                            tma_load_3d(sa + q * 2048, &mapA, full, m0 + 16 * q, k0, bz * p.bmulA);
+                    }
+                    if (B_KC) {
+                        tma_load_3d(sb, &mapB, full, k0, n0, bz * p.bmulB);
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < BN / 16; ++q)
-                        tma_load_3d(sb + q * 2048, &mapB, full, n0 + 16 * q, k0, bz * p.bmulB);
+                        for (int q = 0; q < BN / 16; ++q)
+                            tma_load_3d(sb + q * 2048, &mapB, full, n0 + 16 * q, k0, bz * p.bmulB);
+                    }
                 }
             }
         }
@@ -231,55 +230,69 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 offB[s][kb][ip] = L::A_BYTES + frag_off<B_KC>(wn * WN + ip * 8 + rb, k);
             }
 
-    double acc[TI][TJ][2];
-#pragma unroll
-    for (int i = 0; i < TI; ++i)
-#pragma unroll
-        for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    for (int kt = 0; kt < KT; ++kt) {
-        const int s = kt % STAGES;
-        const uint32_t ph = (uint32_t)((kt / STAGES) & 1);
-        mbar_wait(bar_full + 8 * s, ph);
-        const uint32_t st = smem_base + s * L::STAGE_BYTES;
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-            for (int ss = 0; ss < 2; ++ss) {
-                double a[TI], b[TJ];
-#pragma unroll
-                for (int i = 0; i < TI; ++i)
-                    a[i] = lds64(st + offA[ss][kb][i & 1] + (i >> 1) * 2048);
-#pragma unroll
-                for (int j = 0; j < TJ; ++j)
-                    b[j] = lds64(st + offB[ss][kb][j & 1] + (j >> 1) * 2048);
-#pragma unroll
-                for (int i = 0; i < TI; ++i)
-#pragma unroll
-                    for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-    }
-
-    // ===================================== epilogue ============================================
-    double* __restrict__ Cb = p.C + (long long)bz * p.strideC + (long long)zs * p.strideSplit;
     const double alpha = p.alpha, beta = p.beta;
+    unsigned it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const long long bzs = tile / p.tiles_per_batch;
+        const int rt = (int)(tile - bzs * p.tiles_per_batch);
+        const int bz = (int)(bzs / p.ksplit);
+        const int zs = (int)(bzs - (long long)bz * p.ksplit);
+        int tm, tn;
+        if (p.raster_n_fast) { tm = rt / p.tilesN; tn = rt - tm * p.tilesN; }
+        else { tn = rt / p.tilesM; tm = rt - tn * p.tilesM; }
+        const int m0 = tm * BM, n0 = tn * BN;
+        const int kt_begin = zs * p.kt_per_split;
+        const int KT = min(KT_all - kt_begin, p.kt_per_split);
+
+        double acc[TI][TJ][2];
 #pragma unroll
-    for (int j = 0; j < TJ; ++j) {
+        for (int i = 0; i < TI; ++i)
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int n = n0 + wn * WN + j * 8 + frag_row<B_KC>(2 * t + c);
-            if (n < p.N) {
-                double* col = Cb + (long long)n * p.ldc;
+            for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kt = 0; kt < KT; ++kt, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+            mbar_wait(bar_full + 8 * s, ph);
+            const uint32_t st = smem_base + s * L::STAGE_BYTES;
 #pragma unroll
-                for (int i = 0; i < TI; ++i) {
-                    const int m = m0 + wm * WM + i * 8 + ra;
-                    if (m < p.M) {
-                        double v = alpha * acc[i][j][c];
-                        if (beta != 0.0) v += beta * col[m];
-                        col[m] = v;
+            for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+                for (int ss = 0; ss < 2; ++ss) {
+                    double a[TI], b[TJ];
+#pragma unroll
+                    for (int i = 0; i < TI; ++i)
+                        a[i] = lds64(st + offA[ss][kb][i & 1] + (i >> 1) * 2048);
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j)
+                        b[j] = lds64(st + offB[ss][kb][j & 1] + (j >> 1) * 2048);
+#pragma unroll
+                    for (int i = 0; i < TI; ++i)
+#pragma unroll
+                        for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+        }
+
+        // ================================= epilogue of this tile ================================
+        double* __restrict__ Cb = p.C + (long long)bz * p.strideC + (long long)zs * p.strideSplit;
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int n = n0 + wn * WN + j * 8 + frag_row<B_KC>(2 * t + c);
+                if (n < p.N) {
+                    double* col = Cb + (long long)n * p.ldc;
+#pragma unroll
+                    for (int i = 0; i < TI; ++i) {
+                        const int m = m0 + wm * WM + i * 8 + ra;
+                        if (m < p.M) {
+                            double v = alpha * acc[i][j][c];
+                            if (beta != 0.0) v += beta * col[m];
+                            col[m] = v;
+                        }
                     }
                 }
             }
