@@ -184,7 +184,11 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
     p.total_tiles = total;
     // persistent CTAs (one per SM) once there is more than ~a wave of tiles; otherwise one CTA per tile
     const long long sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
-    const long long grid = persistent_gemm() ? std::min<long long>(total, sms) : total;
+    // Persistent CTAs pay off when tiles are short (few k-stages: the per-tile launch / barrier-init /
+    // first-load latency is a visible fraction; measured +10 % on the quarter transforms, K = N) and
+    // cost ~1-3 % on long-K tiles (static tile assignment, extra live registers), so: short K only.
+    const bool persistent = persistent_gemm() && kt_per_split <= 32 && total > sms;
+    const long long grid = persistent ? sms : total;
     fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(mapA, mapB, p);
     JUES_CUDA(cudaGetLastError());
     ctx->stats.gemm_flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch;
