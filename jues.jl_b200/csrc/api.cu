@@ -11,6 +11,7 @@ using namespace jues;
 namespace {
 
 void begin_call(jues_ctx* ctx) {
+    resolve_timers(ctx);
     ctx->timings.clear();
     ctx->alloc_host_s = 0.0;
     ctx->alloc_calls = 0;

@@ -234,6 +234,7 @@ struct CC {
     ~CC() { ctx->perm_cache = nullptr; pcache.clear(); }
 
     double energy() { return cc_energy(ctx, V.p(), T2.p(), singles ? T1.p() : nullptr, o, v); }
+    void energy_async(double* dev_out) { cc_energy_async(ctx, V.p(), T2.p(), singles ? T1.p() : nullptr, o, v, dev_out); }
 
     void guess(int guess_mode) {
         T2.alloc(ctx, o, o, v, v); T2n.alloc(ctx, o, o, v, v);
@@ -410,22 +411,35 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
         cc.download(singles ? h1.data() : nullptr, h2.data());
         cb(cb_user, it, e, singles ? h1.data() : nullptr, h2.data());
     };
-    res.e_hist[0] = cc.energy();
-    report(0, res.e_hist[0]);
+    // Energies are reduced on the device into e_dev[it] and read back once at the end, so the host
+    // never waits for a sweep (unless a per-sweep amplitude callback wants the values): the launch
+    // queue stays full across sweeps.
+    DBuf e_dev(ctx, (size_t)maxit + 1);
+    cc.energy_async(e_dev.p);
+    if (cb) {
+        res.e_hist[0] = cc.energy();
+        report(0, res.e_hist[0]);
+    }
     for (int it = 1; it <= maxit; ++it) {
         {
             // one timed "step" = one sweep + the energy the reference evaluates every sweep
-            // (RCCSD.jl:104); the energy read-back is the step's device->host result
+            // (RCCSD.jl:104)
             const double f0 = ctx->stats.gemm_flops;
             Timer t(ctx, "cc.iteration");
             cc.iterate();
-            res.e_hist[it] = cc.energy();
+            cc.energy_async(e_dev.p + it);
             t.stop();
             // FP64 flops this rank's GEMM launches executed in the sweep (reported as a pseudo-phase)
             ctx->timings.emplace_back("cc.iteration.gflop", (float)((ctx->stats.gemm_flops - f0) * 1e-9));
         }
-        report(it, res.e_hist[it]);
+        if (cb) {
+            res.e_hist[it] = cc.energy();
+            report(it, res.e_hist[it]);
+        }
     }
+    JUES_CUDA(cudaMemcpyAsync(res.e_hist.data(), e_dev.p, ((size_t)maxit + 1) * sizeof(double),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     res.energy = res.e_hist[maxit];
     cc.download(singles ? T1_out : nullptr, T2_out);
     return res;

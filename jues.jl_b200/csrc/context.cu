@@ -72,6 +72,7 @@ extern "C" int jues_b200_init(jues_ctx** out, int device) {
 extern "C" void jues_b200_finalize(jues_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    resolve_timers(ctx);
     jues::dist_teardown(ctx);
     for (auto& kv : ctx->big_free) cudaFree(kv.second);
     ctx->big_free.clear();
@@ -88,6 +89,8 @@ extern "C" const char* jues_b200_last_error(jues_ctx* ctx) {
 
 extern "C" int jues_b200_get_phases(jues_ctx* ctx, jues_b200_phase* out, int cap) {
     if (!ctx) return JUES_B200_EINVAL;
+    cudaSetDevice(ctx->device);
+    resolve_timers(ctx);
     int n = 0;
     for (auto& kv : ctx->timings) {
         if (out && n < cap) {

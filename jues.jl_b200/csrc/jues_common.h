@@ -82,6 +82,8 @@ struct jues_ctx {
     size_t red_cap = 0;
     // timing records: name -> milliseconds (accumulated), filled by Timer
     std::vector<std::pair<std::string, float>> timings;
+    struct PendingTimer { size_t slot; cudaEvent_t e0, e1; };
+    std::vector<PendingTimer> pending;   // recorded, not yet resolved (see Timer)
     size_t bytes_allocated = 0;
     size_t bytes_peak = 0;
     std::multimap<size_t, double*> big_free;   // cached cudaMalloc blocks (>= 64 MB) by size
@@ -212,6 +214,9 @@ inline void flush_big_cache(jues_ctx* c) {
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // CUDA-event timer writing into ctx->timings.
+// CUDA-event timer writing into ctx->timings.  Non-blocking: the events are recorded on the stream and
+// resolved (one synchronisation) when the phases are read, so timing a phase never stalls the host
+// thread that is feeding the GPU.
 struct Timer {
     jues_ctx* ctx;
     std::string name;
@@ -222,25 +227,31 @@ struct Timer {
         cudaEventCreate(&e1);
         cudaEventRecord(e0, c->stream);
     }
-    float stop() {
-        float ms = 0;
+    void stop() {
         if (open) {
             cudaEventRecord(e1, ctx->stream);
-            cudaEventSynchronize(e1);
-            cudaEventElapsedTime(&ms, e0, e1);
-            ctx->timings.emplace_back(name, ms);
+            ctx->timings.emplace_back(name, -1.0f);
+            ctx->pending.push_back({ctx->timings.size() - 1, e0, e1});
             open = false;
         }
-        return ms;
     }
-    ~Timer() {
-        stop();
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-    }
+    ~Timer() { stop(); }
 };
 
-// JUES_B200_TRACE=1: fine-grained CUDA-event timings (each one synchronises the stream)
+inline void resolve_timers(jues_ctx* ctx) {
+    if (ctx->pending.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& pt : ctx->pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pt.e0, pt.e1);
+        if (pt.slot < ctx->timings.size()) ctx->timings[pt.slot].second = ms;
+        cudaEventDestroy(pt.e0);
+        cudaEventDestroy(pt.e1);
+    }
+    ctx->pending.clear();
+}
+
+// JUES_B200_TRACE=1: fine-grained CUDA-event timings
 struct TraceTimer {
     Timer* t = nullptr;
     TraceTimer(jues_ctx* ctx, const char* name) {

@@ -517,6 +517,15 @@ static int reduction_blocks(jues_ctx* ctx, int64_t v) {
     return (int)blocks;
 }
 
+void cc_energy_async(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v,
+                     double* dev_out) {
+    const int blocks = reduction_blocks(ctx, v);
+    cc_energy_kernel<<<blocks, 256, 0, ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
+    AUX_LAUNCHED(ctx);
+    final_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, blocks, dev_out);
+    AUX_LAUNCHED(ctx);
+}
+
 double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v) {
     const int blocks = reduction_blocks(ctx, v);
     cc_energy_kernel<<<blocks, 256, 0, ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
