@@ -147,6 +147,56 @@ int jues_b200_rccsd_t4(jues_ctx* ctx, const jues_t4* gao,
                        const double* eps, int maxit,
                        double* e_ccsd, double* e_hist, double* T1_out, double* T2_out);
 
+/* ======== SURVEY.md section 8f: the callers either side of the path ====================== */
+
+/* ---- IntegralTransformation.get_fock (src/Backend/IntegralTransformation.jl:119-141) ------ */
+/* f[p,q] = C[mu,p] C[nu,q] hao[mu,nu] + 2 C C Co Co gao[mu,nu,lam,sig] - C C Co Co gao[mu,lam,nu,sig]
+ * hao (nao,nao) core Hamiltonian (Wfn.hao), C (nao,nmo) = Wfn.Ca, Co (nao,nocc) = Wfn.Cao;
+ * f_out (nmo,nmo).  Two N^4 nocc transforms on the device + traces.                           */
+int jues_b200_get_fock(jues_ctx* ctx, const double* gao, int64_t nao, const double* hao,
+                       const double* C, int64_t nmo, const double* Co, int64_t nocc, double* f_out);
+int jues_b200_get_fock_t4(jues_ctx* ctx, const jues_t4* gao, const double* hao,
+                          const double* C, int64_t nmo, const double* Co, int64_t nocc, double* f_out);
+
+/* ---- CoupledCluster.AutoRCCSD.do_rccsd (src/CoupledCluster/AutoRCCSD.jl:193-301) ---------- */
+/* Options = CoupledCluster.defaults (src/CoupledCluster/CoupledCluster.jl:36-43).            */
+typedef struct {
+    int    cc_max_iter;   /* 50     maximum number of sweeps (AutoRCCSD.jl:271)                 */
+    double cc_e_conv;     /* 1e-10  stop when |dE| <= cc_e_conv ...                             */
+    double cc_max_rms;    /* 1e-10  ... and max(r1,r2) <= cc_max_rms, r = ||dT||_2/length(T) (:174-175,270) */
+    int    do_pT;         /* 0      add the perturbative triples (:294-300)                     */
+    int    fcn;           /* 0      number of frozen core orbitals (:216, get_eri fcn=)         */
+    int    diis;          /* 0      accepted and ignored, as in the reference                   */
+} jues_b200_cc_options;
+int jues_b200_cc_default_options(jues_b200_cc_options* opt);
+
+/* RCCSD for a possibly non-canonical RHF reference: the Fock matrix is built from hao and gao
+ * (get_fock), its diagonal gives the resolvents, its off-diagonal blocks enter the amplitude
+ * equations (AutoRCCSD.jl:219-231).  Ca (nao,nmo): all MO coefficients, ndocc doubly occupied first
+ * (Wfn.Ca, Wfn.nalpha); frozen core = the first opt->fcn of them.  Guess T1 = f_ov/d, T2 = <ij|ab>/D.
+ * Outputs: *e_cc correlation energy; *e_pt (T) correction (written only if opt->do_pT; nullable
+ * otherwise); *iterations sweeps done; *converged 1/0 (:288).  e_hist / rms_hist (nullable):
+ * [cc_max_iter+1], entry 0 = energy of the guess / 1.0, entry k = after sweep k (the table the
+ * reference prints, :285).  T1_out (nact,nvir), T2_out (nact,nact,nvir,nvir) nullable,
+ * nact = ndocc - fcn, nvir = nmo - ndocc.  opt == NULL: defaults.                              */
+int jues_b200_auto_rccsd(jues_ctx* ctx, const double* gao, int64_t nao, const double* hao,
+                         const double* Ca, int64_t nmo, int64_t ndocc,
+                         const jues_b200_cc_options* opt,
+                         double* e_cc, double* e_pt, int* iterations, int* converged,
+                         double* e_hist, double* rms_hist, double* T1_out, double* T2_out);
+int jues_b200_auto_rccsd_t4(jues_ctx* ctx, const jues_t4* gao, const double* hao,
+                            const double* Ca, int64_t nmo, int64_t ndocc,
+                            const jues_b200_cc_options* opt,
+                            double* e_cc, double* e_pt, int* iterations, int* converged,
+                            double* e_hist, double* rms_hist, double* T1_out, double* T2_out);
+
+/* ---- PerturbativeTriples.compute_pT (src/CoupledCluster/PerturbativeTriples.jl:35-138) ---- */
+/* Stand-alone (T) from host arrays in the reference's own argument layouts:
+ * T1 (o,v), T2 (o,o,v,v), Vvvvo (v,v,v,o), Vvooo (v,o,o,o), Vvovo (v,o,v,o), fo (o), fv (v).      */
+int jues_b200_compute_pt(jues_ctx* ctx, const double* T1, const double* T2, const double* Vvvvo,
+                         const double* Vvooo, const double* Vvovo, const double* fo, const double* fv,
+                         int64_t nocc, int64_t nvir, double* e_pt);
+
 /* ---- instrumentation (bench.py) ---------------------------------------------------------- */
 /* Statistics of the last entry-point call on this context: CUDA-event milliseconds per phase
  * on the library's stream, FP64 flops issued by the GEMM kernels, kernel launch counts.

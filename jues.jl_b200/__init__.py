@@ -16,6 +16,9 @@ here                             reference
 ``do_rmp2``                      JuES.MollerPlesset.do_rmp2       (RMP2.jl:11-45)
 ``RCCD.do_rccd``                 JuES.CoupledCluster.RCCD.do_rccd  (RCCD.jl:33-83)
 ``RCCSD.do_rccsd``               JuES.CoupledCluster.RCCSD.do_rccsd (RCCSD.jl:33-116)
+``AutoRCCSD.do_rccsd``           JuES.CoupledCluster.AutoRCCSD.do_rccsd (AutoRCCSD.jl:193-301)
+``get_fock``                     JuES.IntegralTransformation.get_fock (IntegralTransformation.jl:119-141)
+``compute_pT``                   JuES.CoupledCluster.PerturbativeTriples.compute_pT (PerturbativeTriples.jl:35-138)
 ``DeviceFourTensor``             JuES.DiskTensors.DiskFourTensor  (DiskFourTensors.jl:5-95)
 ``gemm``                         LinearAlgebra.BLAS.gemm!         (mRCCD.jl:268-485 call sites)
 ===============================  =========================================================
@@ -37,7 +40,7 @@ from . import _lib
 from ._lib import LibraryMissing  # noqa: F401
 
 __all__ = ["Wfn", "Context", "DeviceFourTensor", "tei_transform", "get_eri", "do_rmp2", "RCCD",
-           "RCCSD", "gemm", "JuesError", "LibraryMissing", "default_context", "synth"]
+           "RCCSD", "AutoRCCSD", "get_fock", "compute_pT", "CC_DEFAULTS", "gemm", "JuesError", "LibraryMissing", "default_context", "synth"]
 
 ERROR_NAMES = {-1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENCCL", -5: "ESTATE"}
 
@@ -78,12 +81,22 @@ class Wfn:
     ao_eri: object            # ndarray (nbf,)*4 or DeviceFourTensor (Wavefunction.jl:87 Union)
     nbeta: int = field(default=-1)
     nvirb: int = field(default=-1)
+    # read only by get_fock / AutoRCCSD (Wavefunction.jl:67,77,83)
+    hao: Optional[np.ndarray] = None      # (nbf, nbf) core Hamiltonian
+    Ca: Optional[np.ndarray] = None       # (nbf, nmo) all MO coefficients; default [Cao Cav]
+    energy: float = 0.0                   # reference energy (only printed by the reference)
 
     def __post_init__(self):
         if self.nbeta < 0:
             self.nbeta = self.nalpha
         if self.nvirb < 0:
             self.nvirb = self.nvira
+        if self.Ca is None:
+            self.Ca = np.concatenate([np.asarray(self.Cao), np.asarray(self.Cav)], axis=1)
+
+    @property
+    def Cb(self):
+        return self.Ca
 
     @property
     def Cbo(self):
@@ -526,6 +539,112 @@ class _RCCSD:
 
 RCCD = _RCCD()
 RCCSD = _RCCSD()
+
+
+# ------------------------------------------------------------------------------------------
+# IntegralTransformation.get_fock, CoupledCluster.AutoRCCSD, PerturbativeTriples.compute_pT
+# ------------------------------------------------------------------------------------------
+CC_DEFAULTS = dict(cc_max_iter=50, cc_max_rms=1e-10, cc_e_conv=1e-10, diis=False, do_pT=False, fcn=0)
+"""JuES.CoupledCluster.defaults (CoupledCluster.jl:36-43)."""
+
+
+def get_fock(wfn: Wfn, spin: str = "alpha", ctx: Optional[Context] = None) -> np.ndarray:
+    """IntegralTransformation.get_fock (IntegralTransformation.jl:119-141): MO-basis Fock matrix
+    (nmo, nmo) from wfn.hao, wfn.ao_eri and the occupied orbitals."""
+    if spin.lower() in ("alpha", "up", "a"):
+        Cm, Co = wfn.Ca, wfn.Cao
+    elif spin.lower() in ("beta", "down", "b"):
+        Cm, Co = wfn.Cb, wfn.Cbo
+    else:
+        raise JuesError(-1, f"Invalid Spin option given to JuES.IntegralTransformation.get_fock: {spin}")
+    if wfn.hao is None:
+        raise JuesError(-1, "get_fock needs wfn.hao (core Hamiltonian)")
+    g = wfn.ao_eri
+    nao = g.shape[0]
+    Cm = _f(Cm)
+    nmo = Cm.shape[1]
+    Cm = _f(Cm, (nao, nmo))
+    Co = _f(Co)
+    no = Co.shape[1]
+    Co = _f(Co, (nao, no))
+    h = _f(wfn.hao, (nao, nao))
+    ctx = ctx or (g.ctx if isinstance(g, DeviceFourTensor) else default_context())
+    out = np.empty((nmo, nmo), order="F")
+    if isinstance(g, DeviceFourTensor):
+        ctx._check(ctx._lib.jues_b200_get_fock_t4(ctx._h, g._h, _p(h), _p(Cm), nmo, _p(Co), no, _p(out)))
+    else:
+        g = _f(g, (nao,) * 4)
+        ctx._check(ctx._lib.jues_b200_get_fock(ctx._h, _p(g), nao, _p(h), _p(Cm), nmo, _p(Co), no, _p(out)))
+    return out
+
+
+class _AutoRCCSD:
+    """JuES.CoupledCluster.AutoRCCSD"""
+
+    def do_rccsd(self, wfn: Wfn, ctx: Optional[Context] = None, *, _return_all: bool = False, **kwargs):
+        """AutoRCCSD.do_rccsd (AutoRCCSD.jl:193-301).  Options are JuES.CoupledCluster.defaults
+        (cc_max_iter, cc_e_conv, cc_max_rms, do_pT, fcn, diis); unknown kwargs are ignored like the
+        reference's option loop (:199-205).  The reference returns nothing useful (its last
+        expression is an @output); here the CCSD correlation energy is returned -- plus E(T) when
+        do_pT -- or, with the test hook ``_return_all``, a dict with everything it prints."""
+        opt = dict(CC_DEFAULTS)
+        opt.update({k: v for k, v in kwargs.items() if k in CC_DEFAULTS})
+        nelec = int(wfn.nalpha) + int(wfn.nbeta)
+        if nelec % 2 != 0:                                                          # :209
+            raise JuesError(-1, f"Number of electrons must be even for RHF. Given {nelec}")
+        if wfn.hao is None:
+            raise JuesError(-1, "AutoRCCSD needs wfn.hao (core Hamiltonian) to build the Fock matrix")
+        ndocc = nelec // 2
+        nmo = int(wfn.nmo)
+        g = wfn.ao_eri
+        nao = g.shape[0]
+        Ca = _f(wfn.Ca, (nao, nmo))
+        h = _f(wfn.hao, (nao, nao))
+        ctx = ctx or (g.ctx if isinstance(g, DeviceFourTensor) else default_context())
+        co = _lib.CCOptions(int(opt["cc_max_iter"]), float(opt["cc_e_conv"]), float(opt["cc_max_rms"]),
+                            int(bool(opt["do_pT"])), int(opt["fcn"]), int(bool(opt["diis"])))
+        no, nv = ndocc - co.fcn, nmo - ndocc
+        e, ept = C.c_double(), C.c_double()
+        its, conv = C.c_int(), C.c_int()
+        eh = np.zeros(co.cc_max_iter + 1)
+        rh = np.zeros(co.cc_max_iter + 1)
+        T1 = np.empty((max(no, 0), nv), order="F") if _return_all else None
+        T2 = np.empty((max(no, 0), max(no, 0), nv, nv), order="F") if _return_all else None
+        ctx._cb_shapes(no, nv)
+        tail = (nmo, ndocc, C.byref(co), C.byref(e), C.byref(ept), C.byref(its), C.byref(conv),
+                _p(eh), _p(rh), _p(T1), _p(T2))
+        if isinstance(g, DeviceFourTensor):
+            ctx._check(ctx._lib.jues_b200_auto_rccsd_t4(ctx._h, g._h, _p(h), _p(Ca), *tail))
+        else:
+            g = _f(g, (nao,) * 4)
+            ctx._check(ctx._lib.jues_b200_auto_rccsd(ctx._h, _p(g), nao, _p(h), _p(Ca), *tail))
+        n = its.value
+        if _return_all:
+            return dict(ecc=e.value, ept=ept.value if opt["do_pT"] else None, iterations=n,
+                        converged=bool(conv.value), e_hist=eh[:n + 1].copy(), rms_hist=rh[:n + 1].copy(),
+                        T1=T1, T2=T2)
+        return (e.value, ept.value) if opt["do_pT"] else e.value
+
+
+AutoRCCSD = _AutoRCCSD()
+
+
+def compute_pT(*, T1, T2, Vvvvo, Vvooo, Vvovo, fo, fv, ctx: Optional[Context] = None) -> float:
+    """PerturbativeTriples.compute_pT (PerturbativeTriples.jl:35-138), keyword arguments and array
+    layouts exactly as the reference's."""
+    T1 = _f(T1)
+    o, v = T1.shape
+    T2 = _f(T2, (o, o, v, v))
+    Vvvvo = _f(Vvvvo, (v, v, v, o))
+    Vvooo = _f(Vvooo, (v, o, o, o))
+    Vvovo = _f(Vvovo, (v, o, v, o))
+    fo = _f(fo, (o,))
+    fv = _f(fv, (v,))
+    ctx = ctx or default_context()
+    e = C.c_double()
+    ctx._check(ctx._lib.jues_b200_compute_pt(ctx._h, _p(T1), _p(T2), _p(Vvvvo), _p(Vvooo), _p(Vvovo),
+                                             _p(fo), _p(fv), o, v, C.byref(e)))
+    return e.value
 
 
 def gemm(tA, tB, alpha, A, B, beta=0.0, Cm=None, ctx: Optional[Context] = None):

@@ -18,6 +18,14 @@ class Phase(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("ms", C.c_double)]
 
 
+class CCOptions(C.Structure):
+    """jues_b200_cc_options (CoupledCluster.defaults, CoupledCluster.jl:36-43)."""
+    _fields_ = [("cc_max_iter", C.c_int), ("cc_e_conv", C.c_double), ("cc_max_rms", C.c_double),
+                ("do_pT", C.c_int), ("fcn", C.c_int), ("diis", C.c_int)]
+
+
+c_int_p = C.POINTER(C.c_int)
+
 AMP_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_double, c_double_p, c_double_p)
 
 # name -> (restype, argtypes); every symbol include/jues_b200.h declares
@@ -67,6 +75,19 @@ SIGNATURES = {
     "jues_b200_rccsd_t4": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int64,
                                      c_double_p, C.c_int64, c_double_p, C.c_int,
                                      c_double_p, c_double_p, c_double_p, c_double_p]),
+    "jues_b200_get_fock": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, C.c_int64,
+                                     c_double_p, C.c_int64, c_double_p]),
+    "jues_b200_get_fock_t4": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, C.c_int64,
+                                        c_double_p, C.c_int64, c_double_p]),
+    "jues_b200_cc_default_options": (C.c_int, [C.POINTER(CCOptions)]),
+    "jues_b200_auto_rccsd": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, C.c_int64,
+                                       C.c_int64, C.POINTER(CCOptions), c_double_p, c_double_p, c_int_p,
+                                       c_int_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "jues_b200_auto_rccsd_t4": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, C.c_int64,
+                                          C.c_int64, C.POINTER(CCOptions), c_double_p, c_double_p, c_int_p,
+                                          c_int_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "jues_b200_compute_pt": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                       c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int64, c_double_p]),
     "jues_b200_get_phases": (C.c_int, [C.c_void_p, C.POINTER(Phase), C.c_int]),
     "jues_b200_get_counters": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_int64_p, c_int64_p]),
     "jues_b200_dgemm_bench": (C.c_int, [C.c_void_p, C.c_char, C.c_char, C.c_int64, C.c_int64,

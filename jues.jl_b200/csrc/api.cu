@@ -425,3 +425,184 @@ extern "C" int jues_b200_t4_synth_eri(jues_t4* t, uint64_t seed, double scale) {
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     JUES_API_END(ctx)
 }
+
+// ---------------------------------------------------------------------------------------------
+// get_fock, AutoRCCSD.do_rccsd, compute_pT
+// ---------------------------------------------------------------------------------------------
+#include "pt.h"
+
+extern "C" int jues_b200_cc_default_options(jues_b200_cc_options* opt) {
+    if (!opt) return JUES_B200_EINVAL;
+    // CoupledCluster.defaults (CoupledCluster.jl:36-43)
+    opt->cc_max_iter = 50;
+    opt->cc_e_conv = 1e-10;
+    opt->cc_max_rms = 1e-10;
+    opt->do_pT = 0;
+    opt->fcn = 0;
+    opt->diis = 0;
+    return JUES_B200_OK;
+}
+
+extern "C" int jues_b200_get_fock(jues_ctx* ctx, const double* gao, int64_t nao, const double* hao,
+                                  const double* C, int64_t nmo, const double* Co, int64_t nocc, double* f_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    Timer total(ctx, "total");
+    HostGaoHolder h;
+    make_host_gao(ctx, h, gao, nao, false);
+    Timer t(ctx, "fock.build");
+    fock_dev(ctx, *h.src, hao, C, nmo, Co, nocc, f_out);
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_get_fock_t4(jues_ctx* ctx, const jues_t4* gao, const double* hao, const double* C,
+                                     int64_t nmo, const double* Co, int64_t nocc, double* f_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    check_t4_is_gao(gao);
+    Timer total(ctx, "total");
+    T4Source holder(gao);
+    Timer t(ctx, "fock.build");
+    fock_dev(ctx, *holder.src, hao, C, nmo, Co, nocc, f_out);
+    JUES_API_END(ctx)
+}
+
+namespace {
+void run_auto(jues_ctx* ctx, GaoSource& src, const double* hao, const double* Ca, int64_t nmo, int64_t ndocc,
+              const jues_b200_cc_options* opt_in, double* e_cc, double* e_pt, int* iterations, int* converged,
+              double* e_hist, double* rms_hist, double* T1_out, double* T2_out) {
+    jues_b200_cc_options opt;
+    jues_b200_cc_default_options(&opt);
+    if (opt_in) opt = *opt_in;
+    JUES_REQUIRE(e_cc != nullptr, "null energy output");
+    JUES_REQUIRE(hao && Ca, "null hao / Ca");
+    JUES_REQUIRE(ndocc > 0 && nmo > ndocc, "need 0 < ndocc < nmo");
+    JUES_REQUIRE(opt.fcn >= 0 && opt.fcn < ndocc, "fcn must satisfy 0 <= fcn < ndocc");
+    JUES_REQUIRE(opt.cc_max_iter >= 0, "cc_max_iter must be non-negative");
+    JUES_REQUIRE(!opt.do_pT || e_pt, "do_pT needs an e_pt output");
+    const int64_t nao = src.n, fcn = opt.fcn;
+    const int64_t no = ndocc - fcn, nv = nmo - ndocc;
+    // Fock matrix from ALL doubly occupied orbitals (AutoRCCSD.jl:219; IntegralTransformation.jl:122-138)
+    std::vector<double> f((size_t)(nmo * nmo));
+    {
+        Timer t(ctx, "fock.build");
+        fock_dev(ctx, src, hao, Ca, nmo, Ca, ndocc, f.data());
+    }
+    // resolvents from the diagonal (:222-224,242-244), off-diagonal blocks (:227-231)
+    std::vector<double> eps((size_t)(no + nv)), foo((size_t)(no * no)), fov((size_t)(no * nv)), fvv((size_t)(nv * nv));
+    auto F = [&](int64_t p, int64_t q) { return p == q ? 0.0 : f[(size_t)(p + nmo * q)]; };
+    for (int64_t i = 0; i < no; ++i) eps[i] = f[(size_t)((fcn + i) * (nmo + 1))];
+    for (int64_t a = 0; a < nv; ++a) eps[no + a] = f[(size_t)((ndocc + a) * (nmo + 1))];
+    for (int64_t k = 0; k < no; ++k)
+        for (int64_t i = 0; i < no; ++i) foo[i + no * k] = F(fcn + i, fcn + k);
+    for (int64_t c = 0; c < nv; ++c)
+        for (int64_t k = 0; k < no; ++k) fov[k + no * c] = F(fcn + k, ndocc + c);
+    for (int64_t a = 0; a < nv; ++a)
+        for (int64_t c = 0; c < nv; ++c) fvv[c + nv * a] = F(ndocc + c, ndocc + a);
+    Problem P;
+    setup_problem(ctx, P, nao, Ca + nao * fcn, no, Ca + nao * ndocc, nv, eps.data());
+    AutoOptions ao;
+    ao.max_iter = opt.cc_max_iter; ao.e_conv = opt.cc_e_conv; ao.max_rms = opt.cc_max_rms; ao.do_pT = opt.do_pT != 0;
+    AutoResult r = auto_rccsd_dev(ctx, P, src, foo.data(), fov.data(), fvv.data(), ao, T1_out, T2_out,
+                                  ctx->amp_cb, ctx->amp_user);
+    *e_cc = r.ecc;
+    if (e_pt && r.has_pt) *e_pt = r.ept;
+    if (iterations) *iterations = r.iterations;
+    if (converged) *converged = r.converged ? 1 : 0;
+    for (int k = 0; k <= r.iterations; ++k) {
+        if (e_hist) e_hist[k] = r.e_hist[k];
+        if (rms_hist) rms_hist[k] = r.rms_hist[k];
+    }
+    ctx->timings.emplace_back("alloc.host_ms", (float)(ctx->alloc_host_s * 1e3));
+    ctx->timings.emplace_back("alloc.calls", (float)ctx->alloc_calls);
+}
+}  // namespace
+
+extern "C" int jues_b200_auto_rccsd(jues_ctx* ctx, const double* gao, int64_t nao, const double* hao,
+                                    const double* Ca, int64_t nmo, int64_t ndocc,
+                                    const jues_b200_cc_options* opt, double* e_cc, double* e_pt,
+                                    int* iterations, int* converged, double* e_hist, double* rms_hist,
+                                    double* T1_out, double* T2_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    Timer total(ctx, "total");
+    HostGaoHolder h;
+    make_host_gao(ctx, h, gao, nao, true);
+    run_auto(ctx, *h.src, hao, Ca, nmo, ndocc, opt, e_cc, e_pt, iterations, converged, e_hist, rms_hist,
+             T1_out, T2_out);
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_auto_rccsd_t4(jues_ctx* ctx, const jues_t4* gao, const double* hao, const double* Ca,
+                                       int64_t nmo, int64_t ndocc, const jues_b200_cc_options* opt,
+                                       double* e_cc, double* e_pt, int* iterations, int* converged,
+                                       double* e_hist, double* rms_hist, double* T1_out, double* T2_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    check_t4_is_gao(gao);
+    Timer total(ctx, "total");
+    T4Source holder(gao);
+    run_auto(ctx, *holder.src, hao, Ca, nmo, ndocc, opt, e_cc, e_pt, iterations, converged, e_hist, rms_hist,
+             T1_out, T2_out);
+    JUES_API_END(ctx)
+}
+
+namespace {
+// host (d0,d1,d2,d3) column-major -> zero-padded device tensor (dp0..dp3)
+void upload_padded_t4(jues_ctx* ctx, DTen& dst, const double* host, const int64_t d[4], const int64_t dp[4]) {
+    const size_t n = (size_t)(d[0] * d[1] * d[2] * d[3]);
+    dst.alloc(ctx, dp[0], dp[1], dp[2], dp[3]);
+    dst.buf.zero();
+    DBuf raw(ctx, n);
+    JUES_CUDA(cudaMemcpyAsync(raw.p, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    block_copy(ctx, raw.p, d, dst.p(), dp, d);
+}
+}  // namespace
+
+extern "C" int jues_b200_compute_pt(jues_ctx* ctx, const double* T1, const double* T2, const double* Vvvvo,
+                                    const double* Vvooo, const double* Vvovo, const double* fo,
+                                    const double* fv, int64_t nocc, int64_t nvir, double* e_pt) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    JUES_REQUIRE(T1 && T2 && Vvvvo && Vvooo && Vvovo && fo && fv && e_pt, "null argument");
+    JUES_REQUIRE(nocc > 0 && nvir > 0, "nocc and nvir must be positive");
+    Timer total(ctx, "total");
+    const int64_t o = round_up(nocc, 2), v = round_up(nvir, 2);
+    DTen t1, t2, a, b, c;
+    DTen OAp(ctx, v, v, o, v), Ov(ctx, o, v, o, o), Vv(ctx, v, v, o, o), Tq(ctx, v, v, o, o);
+    {
+        Timer t(ctx, "pt.upload");
+        upload_padded_matrix(ctx, t1.buf, T1, nocc, nvir, o, v);
+        t1.t = Ten(t1.buf.p, o, v);
+        const int64_t d2[4] = {nocc, nocc, nvir, nvir}, p2[4] = {o, o, v, v};
+        upload_padded_t4(ctx, t2, T2, d2, p2);
+        permute_axpby(ctx, 1.0, t2, "ijab", 0.0, Tq, "abji");
+        const int64_t da[4] = {nvir, nvir, nvir, nocc}, pa[4] = {v, v, v, o};
+        upload_padded_t4(ctx, a, Vvvvo, da, pa);                       // Vvvvo[b,d,a,p] = <pd|ab>
+        permute_axpby(ctx, 1.0, a, "bdap", 0.0, OAp, "abpd");
+        a.release();
+        const int64_t db[4] = {nvir, nocc, nocc, nocc}, pb[4] = {v, o, o, o};
+        upload_padded_t4(ctx, b, Vvooo, db, pb);                       // Vvooo[c,r,q,l] = <qr|lc>
+        permute_axpby(ctx, 1.0, b, "crql", 0.0, Ov, "lcqr");
+        const int64_t dc[4] = {nvir, nocc, nvir, nocc}, pc[4] = {v, o, v, o};
+        upload_padded_t4(ctx, c, Vvovo, dc, pc);                       // Vvovo[a,i,b,j] = <ij|ab>
+        permute_axpby(ctx, 1.0, c, "aibj", 0.0, Vv, "abij");
+    }
+    double emin = fo[0], emax = fv[0];
+    for (int64_t k = 0; k < nocc; ++k) emin = std::min(emin, fo[k]);
+    for (int64_t k = 0; k < nvir; ++k) emax = std::max(emax, fv[k]);
+    std::vector<double> eo((size_t)o, emin - 1.0e3), ev((size_t)v, emax + 1.0e3);
+    std::copy(fo, fo + nocc, eo.begin());
+    std::copy(fv, fv + nvir, ev.begin());
+    DBuf eod(ctx, (size_t)o), evd(ctx, (size_t)v);
+    JUES_CUDA(cudaMemcpyAsync(eod.p, eo.data(), o * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    JUES_CUDA(cudaMemcpyAsync(evd.p, ev.data(), v * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    PtInputs in;
+    in.o = o; in.v = v; in.nocc = nocc;
+    in.OAp = OAp.p(); in.Ov = Ov.p(); in.Vv = Vv.p(); in.Tq = Tq.p(); in.t1 = t1.p();
+    in.eo = eod.p; in.ev = evd.p;
+    Timer t(ctx, "pt.energy");
+    *e_pt = pt_dev(ctx, in);
+    JUES_API_END(ctx)
+}

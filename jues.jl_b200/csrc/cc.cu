@@ -15,6 +15,7 @@
 // Every contraction below is one launch of the TMA + DMMA GEMM (contract.cu).
 #include "cc.h"
 #include "dist.h"
+#include "pt.h"
 
 #include <algorithm>
 #include <cmath>
@@ -91,6 +92,48 @@ double rmp2_dev(jues_ctx* ctx, Problem& P, GaoSource& gao) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// get_fock (IntegralTransformation.jl:119-141)
+// ---------------------------------------------------------------------------------------------
+void fock_dev(jues_ctx* ctx, GaoSource& gao, const double* hao, const double* C, int64_t nmo,
+              const double* Co, int64_t nocc, double* f_out) {
+    JUES_REQUIRE(hao && C && Co && f_out, "get_fock: null argument");
+    JUES_REQUIRE(nmo > 0 && nocc > 0, "get_fock: nmo and nocc must be positive");
+    const int64_t n = gao.n, np = gao.np;
+    const int64_t mp = round_up(nmo, 2), op = round_up(nocc, 2);
+    DBuf Cd, Cod, hd;
+    upload_padded_matrix(ctx, Cd, C, n, nmo, np, mp);
+    upload_padded_matrix(ctx, Cod, Co, n, nocc, np, op);
+    upload_padded_matrix(ctx, hd, hao, n, n, np, np);
+    std::vector<double> eye_h((size_t)(op * op), 0.0);
+    for (int64_t k = 0; k < op; ++k) eye_h[k + op * k] = 1.0;
+    DTen f(ctx, mp, mp), tmp(ctx, np, mp), eye(ctx, op, op);
+    JUES_CUDA(cudaMemcpyAsync(eye.p(), eye_h.data(), eye_h.size() * sizeof(double), cudaMemcpyHostToDevice,
+                              ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));   // eye_h is a local vector
+    const Ten Ct(Cd.p, np, mp), ht(hd.p, np, np);
+    // f[p,q] = C[mu,p] C[nu,q] hao[mu,nu]                                               (:136)
+    contract(ctx, 1.0, ht, "mn", Ct, "nq", 0.0, tmp, "mq");
+    contract(ctx, 1.0, Ct, "mp", tmp, "mq", 0.0, f, "pq");
+    {   // + 2 sum_k (pq|kk): the (C,C,Co,Co) transform traced over its occupied pair          (:137)
+        DTen A(ctx, mp, mp, op, op);
+        const double* Cm[4] = {Cd.p, Cd.p, Cod.p, Cod.p};
+        const int64_t dp[4] = {mp, mp, op, op};
+        tei_transform_dev(ctx, gao, Cm, dp, A.p());
+        contract(ctx, 2.0, A, "pqkl", eye, "kl", 1.0, f, "pq");
+    }
+    {   // - sum_k (pk|qk)                                                                     (:138)
+        DTen B(ctx, mp, op, mp, op);
+        const double* Cm[4] = {Cd.p, Cod.p, Cd.p, Cod.p};
+        const int64_t dp[4] = {mp, op, mp, op};
+        tei_transform_dev(ctx, gao, Cm, dp, B.p());
+        contract(ctx, -1.0, B, "pkql", eye, "kl", 1.0, f, "pq");
+    }
+    JUES_CUDA(cudaMemcpy2DAsync(f_out, nmo * 8, f.p(), mp * 8, nmo * 8, nmo, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---------------------------------------------------------------------------------------------
 // coupled cluster
 // ---------------------------------------------------------------------------------------------
 namespace {
@@ -121,6 +164,10 @@ struct CC {
     DTen W4, OA, OB;
     // static combinations
     DTen Vt, oovo, ooov_t;
+    // off-diagonal Fock blocks of a non-canonical reference (AutoRCCSD.jl:218-231), zero diagonals,
+    // zero padding:  foT[m,i] = f[i,m] (o,o),  fov[m,e] (o,v),  fvv[e,a] (v,v).  fock == false: canonical.
+    DTen foT, fov, fvv;
+    bool fock = false;
     // amplitudes (replicated)
     DTen T1, T2, T1n, T2n;
     TransformWorkspace tws;   // shared by the class transforms, released before the sweeps
@@ -291,12 +338,23 @@ struct CC {
         }
         delete tr_small;
         { TraceTimer tt(ctx, "cc.comm.allreduce"); all_reduce_sum(ctx, small.p, small.n); }
+        if (fock) {
+            // one-body terms of a non-canonical reference (AutoRCCSD.jl:78-83,131-136 in the factorised
+            // form of tests/factorized_model.py):  Fae[a,e] += f[e,a] - 1/2 f[m,e] t[m,a],
+            // Fmi[m,i] += f[i,m] + 1/2 f[m,e] t[i,e],  Fme += f[m,e],  R1 += f[i,a]
+            axpby(ctx, (size_t)nFae, 1.0, fvv.p(), 1.0, FaeT.p);
+            contract(ctx, -0.5, fov, "me", t, "ma", 1.0, FaeT, "ea");
+            axpby(ctx, (size_t)nFmi, 1.0, foT.p(), 1.0, Fmi.p);
+            contract(ctx, 0.5, fov, "me", t, "ie", 1.0, Fmi, "mi");
+            axpby(ctx, (size_t)nR1, 1.0, fov.p(), 1.0, R1.p);
+        }
         axpby(ctx, (size_t)nW, 1.0, oooo.p(), 1.0, Wpp.p);
         DTen Fme, FaeT_t, Fmi_t;
         Ten FaeTt = FaeT, FmiT = Fmi;
         if (singles) {
             Fme.alloc(ctx, o, v);
             contract(ctx, 1.0, Vt, "mnef", t, "nf", 0.0, Fme, "me");
+            if (fock) axpby(ctx, (size_t)nR1, 1.0, fov.p(), 1.0, Fme.p());
             contract(ctx, 1.0, ooov_t, "mnie", t, "ne", 1.0, Fmi, "mi");
             contract(ctx, 1.0, ooov, "mnie", t, "je", 1.0, Wpp, "mnij");
             contract(ctx, 1.0, oovo, "mnej", t, "ie", 1.0, Wpp, "mnij");
@@ -373,6 +431,55 @@ struct CC {
         if (singles) { std::swap(T1.buf, T1n.buf); std::swap(T1.t, T1n.t); }
     }
 
+    // Off-diagonal Fock blocks (host, unpadded, diagonals already removed by the caller):
+    // foo (nocc,nocc) indexed [i,k], fov (nocc,nvir) [k,c], fvv (nvir,nvir) [c,a] as AutoRCCSD.jl uses them.
+    void set_fock(const double* foo, const double* fov_h, const double* fvv_h) {
+        JUES_REQUIRE(singles, "off-diagonal Fock terms need the singles equations");
+        JUES_REQUIRE(foo && fov_h && fvv_h, "null Fock block");
+        const int64_t no = P.nocc, nv = P.nvir;
+        std::vector<double> fT((size_t)(no * no));
+        for (int64_t i = 0; i < no; ++i)
+            for (int64_t m = 0; m < no; ++m) fT[m + no * i] = foo[i + no * m];   // foT[m,i] = f[i,m]
+        DBuf a, b, c;
+        upload_padded_matrix(ctx, a, fT.data(), no, no, o, o);
+        upload_padded_matrix(ctx, b, fov_h, no, nv, o, v);
+        upload_padded_matrix(ctx, c, fvv_h, nv, nv, v, v);
+        JUES_CUDA(cudaStreamSynchronize(ctx->stream));   // fT is a stack-owned vector
+        foT.buf = std::move(a); foT.t = Ten(foT.buf.p, o, o);
+        fov.buf = std::move(b); fov.t = Ten(fov.buf.p, o, v);
+        fvv.buf = std::move(c); fvv.t = Ten(fvv.buf.p, v, v);
+        fock = true;
+    }
+
+    // E(T) from the current amplitudes (PerturbativeTriples.jl:35-138 through pt.cu).  Destroys the
+    // integral classes the triples do not read; call after the last sweep.
+    double triples() {
+        JUES_REQUIRE(singles, "(T) needs the RCCSD integral classes");
+        pcache.clear();
+        W4.release(); OB.release(); J.release(); oooo.release(); Vt.release(); oovo.release(); ooov_t.release();
+        T2n.release();
+        DTen OAfull;
+        const double* OAp = OA.p();          // OA[e,f,m,b] = <ef|mb> = <mb|ef>: already OAp[a,b,p,d]
+        if (ctx->nranks > 1) {
+            const size_t cnt = (size_t)(v * v * o * vs);
+            OAfull.alloc(ctx, v, v, o, v);
+            JUES_CUDA(cudaMemcpyAsync(OAfull.p() + (size_t)ctx->rank * cnt, OA.p(), cnt * sizeof(double),
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+            all_gather_inplace(ctx, OAfull.p(), cnt);
+            OA.release();
+            OAp = OAfull.p();
+        }
+        DTen Ov(ctx, o, v, o, o), Vv(ctx, v, v, o, o), Tq(ctx, v, v, o, o);
+        permute_axpby(ctx, 1.0, ooov, "qrlc", 0.0, Ov, "lcqr");
+        permute_axpby(ctx, 1.0, V, "ijab", 0.0, Vv, "abij");
+        permute_axpby(ctx, 1.0, T2, "ijab", 0.0, Tq, "abji");
+        PtInputs in;
+        in.o = o; in.v = v; in.nocc = P.nocc;
+        in.OAp = OAp; in.Ov = Ov.p(); in.Vv = Vv.p(); in.Tq = Tq.p(); in.t1 = T1.p();
+        in.eo = P.eo.p; in.ev = P.ev.p;
+        return pt_dev(ctx, in);
+    }
+
     // host copies in the caller's (unpadded) layout
     void download(double* T1_host, double* T2_host) {
         if (T2_host) {
@@ -442,6 +549,85 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     res.energy = res.e_hist[maxit];
     cc.download(singles ? T1_out : nullptr, T2_out);
+    return res;
+}
+
+// AutoRCCSD.do_rccsd (AutoRCCSD.jl:193-301): RCCSD for a possibly non-canonical reference with real
+// convergence control.  P.eo / P.ev hold the DIAGONAL of the Fock matrix (the resolvents d, D of
+// :242-244); foo/fov/fvv its off-diagonal blocks.  The sweep is the same factorised sweep as
+// do_rccsd plus the one-body terms; per sweep the host reads back three doubles (energy and the two
+// squared amplitude changes) to take the reference's stop decision (:270-285).
+AutoResult auto_rccsd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, const double* foo, const double* fov,
+                          const double* fvv, const AutoOptions& opt, double* T1_out, double* T2_out,
+                          jues_b200_amp_cb cb, void* cb_user) {
+    JUES_REQUIRE(opt.max_iter >= 0, "cc_max_iter must be non-negative");
+    CC cc(ctx, P, true);
+    cc.set_fock(foo, fov, fvv);
+    cc.build_integrals(gao);
+    cc.register_static();
+    cc.guess(1);                                                              // T2 = <ij|ab>/D (:247)
+    divide_Dia(ctx, cc.fov.p(), cc.T1.p(), P.eo.p, P.ev.p, cc.o, cc.v);       // T1 = f_ov/d    (:246)
+    const size_t n1 = (size_t)(cc.o * cc.v), n2 = (size_t)(cc.o * cc.o * cc.v * cc.v);
+    const double len1 = (double)(P.nocc * P.nvir), len2 = (double)(P.nocc * P.nocc) * (double)(P.nvir * P.nvir);
+    DBuf scal(ctx, 4);
+    double h[3] = {0, 0, 0};
+    auto energy = [&]() {
+        // update_energy (:40-52):  2 f_kc t_kc + sum <kl|cd> (2 tau_klcd - tau_lkcd)
+        cc.energy_async(scal.p);
+        dot_axpby(ctx, n1, 2.0, cc.fov.p(), cc.T1.p(), 1.0, scal.p);
+    };
+    auto read = [&](int n) {
+        JUES_CUDA(cudaMemcpyAsync(h, scal.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    };
+    std::vector<double> h1, h2;
+    auto report = [&](int it, double e) {
+        if (!cb) return;
+        h2.resize((size_t)(P.nocc * P.nocc * P.nvir * P.nvir));
+        h1.resize((size_t)(P.nocc * P.nvir));
+        cc.download(h1.data(), h2.data());
+        cb(cb_user, it, e, h1.data(), h2.data());
+    };
+    AutoResult res;
+    energy();
+    read(1);
+    double Ecc = h[0];
+    res.e_hist.push_back(Ecc);
+    res.rms_hist.push_back(1.0);
+    report(0, Ecc);
+    double dE = 1.0, rms = 1.0;
+    int ite = 1;
+    while (std::fabs(dE) > opt.e_conv || rms > opt.max_rms) {                 // :270
+        if (ite > opt.max_iter) break;                                        // :271-274
+        {
+            const double f0 = ctx->stats.gemm_flops;
+            Timer t(ctx, "cc.iteration");
+            cc.iterate();                       // afterwards T1/T2 are the new, T1n/T2n the old amplitudes
+            sqdiff_async(ctx, n1, cc.T1.p(), cc.T1n.p(), scal.p + 1);         // :174-175
+            sqdiff_async(ctx, n2, cc.T2.p(), cc.T2n.p(), scal.p + 2);
+            energy();
+            t.stop();
+            ctx->timings.emplace_back("cc.iteration.gflop", (float)((ctx->stats.gemm_flops - f0) * 1e-9));
+        }
+        read(3);
+        rms = std::max(std::sqrt(h[1]) / len1, std::sqrt(h[2]) / len2);       // :278
+        const double oldE = Ecc;
+        Ecc = h[0];
+        dE = Ecc - oldE;
+        res.e_hist.push_back(Ecc);
+        res.rms_hist.push_back(rms);
+        report(ite, Ecc);
+        ++ite;
+    }
+    res.iterations = ite - 1;
+    res.converged = std::fabs(dE) < opt.e_conv && rms < opt.max_rms;          // :288
+    res.ecc = Ecc;
+    cc.download(T1_out, T2_out);
+    if (opt.do_pT) {                                                          // :294-300
+        Timer t(ctx, "cc.triples");
+        res.ept = cc.triples();
+        res.has_pt = true;
+    }
     return res;
 }
 

@@ -30,4 +30,27 @@ double rmp2_dev(jues_ctx* ctx, Problem& P, GaoSource& gao);
 CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int maxit, int guess_mode,
                 double* T1_out, double* T2_out, jues_b200_amp_cb cb, void* cb_user);
 
+// AutoRCCSD.do_rccsd (AutoRCCSD.jl:193-301; options CoupledCluster.jl:36-43)
+struct AutoOptions {
+    int max_iter = 50;
+    double e_conv = 1e-10, max_rms = 1e-10;
+    bool do_pT = false;
+};
+struct AutoResult {
+    double ecc = 0.0, ept = 0.0;
+    bool has_pt = false, converged = false;
+    int iterations = 0;
+    std::vector<double> e_hist, rms_hist;   // [iterations + 1]; entry 0 = MP2 guess / 1.0
+};
+// foo (nocc,nocc), fov (nocc,nvir), fvv (nvir,nvir): HOST, off-diagonal Fock blocks (zero diagonals);
+// P.eo / P.ev: the Fock diagonal.  T1_out/T2_out: HOST, unpadded, nullable.
+AutoResult auto_rccsd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, const double* foo, const double* fov,
+                          const double* fvv, const AutoOptions& opt, double* T1_out, double* T2_out,
+                          jues_b200_amp_cb cb, void* cb_user);
+
+// get_fock (IntegralTransformation.jl:119-141): f = C^T h C + 2 sum_k (pq|kk) - sum_k (pk|qk), k over the
+// columns of Co.  hao (nao,nao), C (nao,nmo), Co (nao,nocc): HOST; f_out (nmo,nmo): HOST.
+void fock_dev(jues_ctx* ctx, GaoSource& gao, const double* hao, const double* C, int64_t nmo,
+              const double* Co, int64_t nocc, double* f_out);
+
 }  // namespace jues

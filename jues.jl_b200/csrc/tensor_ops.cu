@@ -302,6 +302,26 @@ __global__ void final_reduce_kernel(const double* __restrict__ partial, int n, d
     if (threadIdx.x == 0) out[0] = r;
 }
 
+__global__ void dot_axpby_kernel(const double* __restrict__ x, const double* __restrict__ y, long long n,
+                                 double alpha, double beta, double* __restrict__ out) {
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += x[i] * y[i];
+    const double r = block_reduce<256>(acc);
+    if (threadIdx.x == 0) out[0] = alpha * r + (beta == 0.0 ? 0.0 : beta * out[0]);
+}
+
+__global__ void sqdiff_kernel(const double* __restrict__ x, const double* __restrict__ y, long long n,
+                              double* __restrict__ partial) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double d = x[i] - y[i];
+        acc += d * d;
+    }
+    const double r = block_reduce<256>(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
 __global__ void synth_eri_kernel(double* __restrict__ g, long long n, long long np, long long lam_lo,
                                  long long lam_count, long long sig_lo, long long sig_count,
                                  unsigned long long seed, double scale, int phys) {
@@ -543,6 +563,21 @@ double mp2_energy(jues_ctx* ctx, const double* V, const double* eo, const double
                                                                   ctx->red_dev);
     AUX_LAUNCHED(ctx);
     return finish_reduction(ctx, (int)blocks);
+}
+
+void dot_axpby(jues_ctx* ctx, size_t n, double alpha, const double* x, const double* y, double beta,
+               double* dev_out) {
+    dot_axpby_kernel<<<1, 256, 0, ctx->stream>>>(x, y, (long long)n, alpha, beta, dev_out);
+    AUX_LAUNCHED(ctx);
+}
+
+void sqdiff_async(jues_ctx* ctx, size_t n, const double* x, const double* y, double* dev_out) {
+    int blocks = ew_grid(ctx, n, 256);
+    if (blocks > (int)ctx->red_cap - 4) blocks = (int)ctx->red_cap - 4;
+    sqdiff_kernel<<<blocks, 256, 0, ctx->stream>>>(x, y, (long long)n, ctx->red_dev);
+    AUX_LAUNCHED(ctx);
+    final_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, blocks, dev_out);
+    AUX_LAUNCHED(ctx);
 }
 
 void block_copy(jues_ctx* ctx, const double* src, const int64_t sd[4], double* dst, const int64_t dd[4],

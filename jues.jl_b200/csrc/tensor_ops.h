@@ -83,6 +83,12 @@ void cc_energy_async(jues_ctx* ctx, const double* V, const double* T, const doub
 double mp2_energy(jues_ctx* ctx, const double* v, const double* eo, const double* ev, int64_t o, int64_t vv,
                   int64_t b0, int64_t vs);
 
+// dev_out[0] = alpha * sum_k x[k] y[k] + beta * dev_out[0]   (one block, fixed order; for o*v-sized vectors)
+void dot_axpby(jues_ctx* ctx, size_t n, double alpha, const double* x, const double* y, double beta,
+               double* dev_out);
+// dev_out[0] = sum_k (x[k] - y[k])^2   (deterministic two-pass tree, no host synchronisation)
+void sqdiff_async(jues_ctx* ctx, size_t n, const double* x, const double* y, double* dev_out);
+
 // counter-based synthetic ERIs (same function as jues.jl_b200.synth.counter_eri_element)
 void synth_eri_fill(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t sig_lo,
                     int64_t sig_count, unsigned long long seed, double scale, bool phys = false);

@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = ["dense_eri", "orbitals", "dense_inputs", "counter_eri", "counter_eri_element", "counter_scale",
-           "default_scale"]
+           "default_scale", "core_hamiltonian", "noncanonical_inputs"]
 
 _MASK = (1 << 64) - 1
 
@@ -64,6 +64,39 @@ def dense_inputs(nbf: int, nocc: int, seed: int = 2024, scale: float | None = No
     gao = dense_eri(nbf, seed, scale)
     Cao, Cav, eps = orbitals(nbf, nocc, seed)
     return gao, Cao, Cav, eps
+
+
+def core_hamiltonian(gao, Cao, Cav, eps) -> np.ndarray:
+    """The hao for which (Cao, Cav, eps) IS the converged RHF solution of the synthetic gao:
+    hao = C diag(eps) C^T - G[D], G = 2J - K of the density of Cao (C is orthogonal), so that
+    get_fock (IntegralTransformation.jl:119-141) returns diag(eps) in the basis of C.  Input
+    plumbing for the AutoRCCSD shapes (N^4 numpy work, N <~ 200)."""
+    C = np.concatenate([Cao, Cav], axis=1)
+    D = Cao @ Cao.T
+    G = 2.0 * np.einsum("mnls,ls->mn", gao, D, optimize=True) - np.einsum("mlns,ls->mn", gao, D, optimize=True)
+    return np.asfortranarray(C @ np.diag(eps) @ C.T - G)
+
+
+def noncanonical_inputs(nbf: int, nocc: int, seed: int = 2024, scale: float | None = None,
+                        ov_mix: float = 0.0):
+    """-> (gao, hao, Ca, eps_canonical): the `dense_inputs` problem with its occupied orbitals
+    rotated among themselves and its virtuals among themselves by random orthogonal matrices
+    (a non-canonical RHF reference: f_oo, f_vv off-diagonal != 0, f_ov = 0, same CCSD energy),
+    plus an optional occupied-virtual rotation of angle ~ov_mix (f_ov != 0: not an RHF solution
+    any more, but a valid input of AutoRCCSD's equations)."""
+    gao, Cao, Cav, eps = dense_inputs(nbf, nocc, seed, scale)
+    hao = core_hamiltonian(gao, Cao, Cav, eps)
+    rng = np.random.default_rng(seed + 7_000_003)
+    Uo, _ = np.linalg.qr(rng.standard_normal((nocc, nocc)))
+    Uv, _ = np.linalg.qr(rng.standard_normal((nbf - nocc, nbf - nocc)))
+    Ca = np.concatenate([Cao @ Uo, Cav @ Uv], axis=1)
+    if ov_mix:
+        K = rng.standard_normal((nbf, nbf)) * ov_mix
+        K = K - K.T
+        # orthogonal rotation exp(K) by its Cayley transform (orthogonal to rounding)
+        I = np.eye(nbf)
+        Ca = Ca @ np.linalg.solve(I - 0.5 * K, I + 0.5 * K)
+    return gao, hao, np.asfortranarray(Ca), eps
 
 
 # ---------------------------------------------------------------------------------------

@@ -72,12 +72,18 @@ class Wfn:
     # beta fields mirror alpha for a restricted reference (Wavefunction.jl:106-113)
     nbeta: int = field(default=-1)
     nvirb: int = field(default=-1)
+    # read only by get_fock / AutoRCCSD (Wavefunction.jl:67,77,83; IntegralTransformation.jl:119-141)
+    hao: Optional[np.ndarray] = None      # (nbf, nbf) core Hamiltonian
+    Ca: Optional[np.ndarray] = None       # (nbf, nmo) = [Cao Cav] (Wavefunction.jl:113-118)
+    energy: float = 0.0                   # reference (SCF) energy, only printed
 
     def __post_init__(self):
         if self.nbeta < 0:
             self.nbeta = self.nalpha
         if self.nvirb < 0:
             self.nvirb = self.nvira
+        if self.Ca is None:
+            self.Ca = np.concatenate([np.asarray(self.Cao), np.asarray(self.Cav)], axis=1)
 
     @property
     def Cbo(self):
@@ -86,6 +92,10 @@ class Wfn:
     @property
     def Cbv(self):
         return self.Cav
+
+    @property
+    def Cb(self):
+        return self.Ca
 
     @property
     def nmo(self):

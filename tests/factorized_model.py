@@ -63,7 +63,10 @@ def rccd_iteration(I, T, D):
 # ------------------------------------------------------------------------------------------
 # RCCSD
 # ------------------------------------------------------------------------------------------
-def rccsd_iteration(I, t, T, Dia, D):
+def rccsd_iteration(I, t, T, Dia, D, fock=None):
+    """fock = (foo, fov, fvv): off-diagonal Fock blocks (zero diagonals) of a non-canonical
+    reference, index order as AutoRCCSD.jl:78-80,130-131 uses them (foo[i,k], fov[k,c], fvv[c,a]).
+    None = canonical orbitals (RCCSD.jl)."""
     V, J, ooov, ovvv, oooo, vvvv = (I[k] for k in ("V", "J", "ooov", "ovvv", "oooo", "vvvv"))
     # ---- static combinations (built once in the library) ----
     Vt = 2 * V - V.transpose(1, 0, 2, 3)
@@ -80,6 +83,13 @@ def rccsd_iteration(I, t, T, Dia, D):
     Fme = es("mnef,nf->me", Vt, t)
     Fae = es("maef,mf->ae", Ot, t) - es("mnaf,mnef->ae", tauh, Vt)
     Fmi = es("mnie,ne->mi", ooov_t, t) + es("inef,mnef->mi", tauh, Vt)
+    R1f = 0.0
+    if fock is not None:
+        foo, fov, fvv = fock
+        Fae = Fae + fvv.T - 0.5 * es("me,ma->ae", fov, t)       # Fae[a,e] += f[e,a] - 1/2 f[m,e] t[m,a]
+        Fmi = Fmi + foo.T + 0.5 * es("me,ie->mi", fov, t)       # Fmi[m,i] += f[i,m] + 1/2 f[m,e] t[i,e]
+        Fme = Fme + fov
+        R1f = fov
     Fae_t = Fae - 0.5 * es("mb,me->be", t, Fme)
     Fmi_t = Fmi + 0.5 * es("je,me->mj", t, Fme)
     X = 0.5 * es("mnef,ijef->mnij", V, tau)
@@ -90,7 +100,7 @@ def rccsd_iteration(I, t, T, Dia, D):
     WmBEj = (-J.transpose(0, 1, 3, 2) - es("mbfe,jf->mbej", ovvv, t) + es("nmej,nb->mbej", oovo, t)
              + es("nmef,jnfb->mbej", V, 0.5 * T + tt))
     # ---- T1 ----
-    R1 = (es("ie,ae->ia", t, Fae) - es("ma,mi->ia", t, Fmi) + es("imae,me->ia", Tt, Fme)
+    R1 = (R1f + es("ie,ae->ia", t, Fae) - es("ma,mi->ia", t, Fmi) + es("imae,me->ia", Tt, Fme)
           + es("imae,me->ia", 2 * V, t) - es("maie,me->ia", J, t)
           - es("mnae,mnie->ia", T, ooov_t) + es("imef,maef->ia", T, Ot))
     # ---- T2: ladders ----

@@ -56,8 +56,10 @@ def rank_integrals(I, b0, b1):
     return R
 
 
-def sweep(R, t, T, eo, ev, b0, b1, comm=None, singles=True):
-    """One Jacobi sweep; returns (t_new, T_new) replicated on every rank."""
+def sweep(R, t, T, eo, ev, b0, b1, comm=None, singles=True, fock=None):
+    """One Jacobi sweep; returns (t_new, T_new) replicated on every rank.
+    fock = (foo, fov, fvv): off-diagonal Fock blocks of a non-canonical reference (AutoRCCSD),
+    replicated on every rank, added once after the all-reduce exactly as cc.cu does."""
     comm = comm or SoloComm()
     S = slice(b0, b1)
     V, J, oooo, ooov = R["V"], R["J"], R["oooo"], R["ooov"]
@@ -89,8 +91,15 @@ def sweep(R, t, T, eo, ev, b0, b1, comm=None, singles=True):
     Wpp = buf[v * v + o * o:v * v + o * o + o ** 4].reshape(o, o, o, o) + oooo
     R1 = buf[v * v + o * o + o ** 4:].reshape(o, v)
     t_new = t
+    if fock is not None:
+        foo, fov, fvv = fock
+        FaeT = FaeT + fvv - 0.5 * es("me,ma->ea", fov, t)          # FaeT[e,a] = Fae[a,e]
+        Fmi = Fmi + foo.T + 0.5 * es("me,ie->mi", fov, t)
+        R1 = R1 + fov
     if singles:
         Fme = es("mnef,nf->me", Vt, t)
+        if fock is not None:
+            Fme = Fme + fock[1]
         Fmi = Fmi + es("mnie,ne->mi", ooov_t, t)
         Wpp = Wpp + es("mnie,je->mnij", ooov, t) + es("mnej,ie->mnij", oovo, t)
         R1 = (R1 + es("ie,ea->ia", t, FaeT) - es("ma,mi->ia", t, Fmi) + es("imae,me->ia", Tt, Fme)
