@@ -9,6 +9,9 @@
 #     JuES.CoupledCluster.RCCSD.do_rccsd(refWfn::Wfn; kwargs...)  (src/CoupledCluster/RCCSD.jl:33)
 #     JuES.Transformation.tei_transform(gao, C1, C2, C3, C4, name) (src/Backend/Transformation.jl:39)
 #     JuES.IntegralTransformation.get_eri(wfn, str; notation, fcn) (src/Backend/IntegralTransformation.jl:38)
+#     JuES.IntegralTransformation.get_fock(wfn; spin)              (src/Backend/IntegralTransformation.jl:119)
+#     JuES.CoupledCluster.AutoRCCSD.do_rccsd(wfn; kwargs...)       (src/CoupledCluster/AutoRCCSD.jl:193)
+#     JuES.CoupledCluster.PerturbativeTriples.compute_pT(; ...)    (src/CoupledCluster/PerturbativeTriples.jl:35)
 #
 # dispatch to the device when the backend switch is :b200 -- selected with the environment
 # variable JUES_BACKEND=b200 (read at load time) or `JuESB200.set_backend(:b200)`, the twin of
@@ -200,6 +203,90 @@ function do_rccsd(refWfn; kwargs...)                                  # kwargs i
     # the reference prints "@MP2" and one line per sweep through JuES.Output (RCCSD.jl:84,104,110);
     # the JuES-side patch of INTEGRATION.md forwards `hist` to @output so the log lines are unchanged
     e[], hist
+end
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md section 8f: get_fock, AutoRCCSD.do_rccsd, compute_pT
+# ------------------------------------------------------------------------------------------------
+function get_fock(wfn; spin = "alpha")                                # IntegralTransformation.jl:119-141
+    if lowercase(spin) in ["alpha", "up", "a"]
+        C, Co = wfn.Ca, wfn.Cao
+    elseif lowercase(spin) in ["beta", "down", "b"]
+        C, Co = wfn.Cb, wfn.Cbo
+    else
+        error("Invalid Spin option given to JuES.IntegralTransformation.get_fock: $spin")
+    end
+    g = wfn.ao_eri
+    nmo = size(C, 2)
+    f = Array{Float64}(undef, nmo, nmo)
+    if g isa DeviceFourTensor
+        check(ccall(sym(:jues_b200_get_fock_t4), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}),
+                    ctx[], g.h, wfn.hao, C, nmo, Co, size(Co, 2), f))
+    else
+        check(ccall(sym(:jues_b200_get_fock), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}),
+                    ctx[], g, size(g, 1), wfn.hao, C, nmo, Co, size(Co, 2), f))
+    end
+    f
+end
+
+# mirror of `jues_b200_cc_options` (include/jues_b200.h) = JuES.CoupledCluster.defaults (CoupledCluster.jl:36-43)
+struct CCOptions
+    cc_max_iter::Cint
+    cc_e_conv::Cdouble
+    cc_max_rms::Cdouble
+    do_pT::Cint
+    fcn::Cint
+    diis::Cint
+end
+
+"""
+    auto_rccsd(wfn; kwargs...) -> (Ecc, Ept or nothing, iterations, converged, e_hist, rms_hist)
+
+Device twin of `AutoRCCSD.do_rccsd` (AutoRCCSD.jl:193-301).  `kwargs` are the JuES options
+(`cc_max_iter`, `cc_e_conv`, `cc_max_rms`, `do_pT`, `fcn`, `diis`); missing ones take
+`JuES.CoupledCluster.defaults`, unknown ones are ignored like the reference's option loop (:199-205).
+The JuES-side patch (INTEGRATION.md) prints the iteration table from `e_hist`/`rms_hist`.
+"""
+function auto_rccsd(wfn; kwargs...)
+    d = Dict(:cc_max_iter => 50, :cc_max_rms => 10^-10, :cc_e_conv => 10^-10, :diis => false,
+             :do_pT => false, :fcn => 0)
+    for (k, v) in kwargs
+        haskey(d, k) && (d[k] = v)
+    end
+    nelec = wfn.nalpha + wfn.nbeta
+    nelec % 2 == 0 ? nothing : error("Number of electrons must be even for RHF. Given $nelec")   # :209
+    ndocc = Int(nelec / 2)
+    opt = Ref(CCOptions(d[:cc_max_iter], d[:cc_e_conv], d[:cc_max_rms], d[:do_pT] ? 1 : 0, d[:fcn], d[:diis] ? 1 : 0))
+    e = Ref{Float64}(0.0); ept = Ref{Float64}(0.0)
+    its = Ref{Cint}(0); conv = Ref{Cint}(0)
+    eh = zeros(Int(d[:cc_max_iter]) + 1); rh = zeros(Int(d[:cc_max_iter]) + 1)
+    g = wfn.ao_eri
+    if g isa DeviceFourTensor
+        check(ccall(sym(:jues_b200_auto_rccsd_t4), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ref{CCOptions},
+                     Ref{Float64}, Ref{Float64}, Ref{Cint}, Ref{Cint}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    ctx[], g.h, wfn.hao, wfn.Ca, wfn.nmo, ndocc, opt, e, ept, its, conv, eh, rh, C_NULL, C_NULL))
+    else
+        check(ccall(sym(:jues_b200_auto_rccsd), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ref{CCOptions},
+                     Ref{Float64}, Ref{Float64}, Ref{Cint}, Ref{Cint}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    ctx[], g, size(g, 1), wfn.hao, wfn.Ca, wfn.nmo, ndocc, opt, e, ept, its, conv, eh, rh, C_NULL, C_NULL))
+    end
+    n = Int(its[])
+    e[], (d[:do_pT] ? ept[] : nothing), n, conv[] == 1, eh[1:n+1], rh[1:n+1]
+end
+
+function compute_pT(; T1::Array{Float64,2}, T2::Array{Float64,4}, Vvvvo::Array{Float64,4},
+                    Vvooo::Array{Float64,4}, Vvovo::Array{Float64,4}, fo::Array{Float64,1}, fv::Array{Float64,1})
+    o, v = size(T1)                                                   # PerturbativeTriples.jl:39
+    e = Ref{Float64}(0.0)
+    check(ccall(sym(:jues_b200_compute_pt), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Float64}, Int64, Int64, Ref{Float64}),
+                ctx[], T1, T2, Vvvvo, Vvooo, Vvovo, fo, fv, o, v, e))
+    e[]
 end
 
 end # module
