@@ -197,6 +197,23 @@ int jues_b200_compute_pt(jues_ctx* ctx, const double* T1, const double* T2, cons
                          const double* Vvooo, const double* Vvovo, const double* fo, const double* fv,
                          int64_t nocc, int64_t nvir, double* e_pt);
 
+/* ---- CoupledCluster.mRCCD.do_rccd (src/CoupledCluster/mRCCD.jl:37-120, 143-207) ---------- */
+/* RCCD from zero amplitudes with the reference's DIIS: at most 6 vectors kept in Float32, B
+ * normalised by max|B|, Float32 solve, stop when ||T2new - T2old||_2 < 1e-7 or after maxit sweeps
+ * (maxit IS an honoured keyword of this entry point, mRCCD.jl:37).  *iterations: sweeps done;
+ * rms_hist / e_hist (nullable): [maxit] norm of the un-extrapolated change / energy after the
+ * extrapolation, per sweep.  T2_out nullable (return_T2).  Amplitudes carry Float32 rounding by
+ * construction (the extrapolated T2 is a combination of Float32 vectors): parity with the CPU path
+ * is bounded by that, not by FP64 round-off.                                                  */
+int jues_b200_mrccd(jues_ctx* ctx, const double* gao, int64_t nao,
+                    const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                    const double* eps, int maxit,
+                    double* e_ccd, int* iterations, double* rms_hist, double* e_hist, double* T2_out);
+int jues_b200_mrccd_t4(jues_ctx* ctx, const jues_t4* gao,
+                       const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                       const double* eps, int maxit,
+                       double* e_ccd, int* iterations, double* rms_hist, double* e_hist, double* T2_out);
+
 /* ---- instrumentation (bench.py) ---------------------------------------------------------- */
 /* Statistics of the last entry-point call on this context: CUDA-event milliseconds per phase
  * on the library's stream, FP64 flops issued by the GEMM kernels, kernel launch counts.

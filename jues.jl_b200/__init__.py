@@ -17,6 +17,7 @@ here                             reference
 ``RCCD.do_rccd``                 JuES.CoupledCluster.RCCD.do_rccd  (RCCD.jl:33-83)
 ``RCCSD.do_rccsd``               JuES.CoupledCluster.RCCSD.do_rccsd (RCCSD.jl:33-116)
 ``AutoRCCSD.do_rccsd``           JuES.CoupledCluster.AutoRCCSD.do_rccsd (AutoRCCSD.jl:193-301)
+``mRCCD.do_rccd``                JuES.CoupledCluster.mRCCD.do_rccd (mRCCD.jl:37-120; Float32 DIIS :143-207)
 ``get_fock``                     JuES.IntegralTransformation.get_fock (IntegralTransformation.jl:119-141)
 ``compute_pT``                   JuES.CoupledCluster.PerturbativeTriples.compute_pT (PerturbativeTriples.jl:35-138)
 ``DeviceFourTensor``             JuES.DiskTensors.DiskFourTensor  (DiskFourTensors.jl:5-95)
@@ -40,7 +41,7 @@ from . import _lib
 from ._lib import LibraryMissing  # noqa: F401
 
 __all__ = ["Wfn", "Context", "DeviceFourTensor", "tei_transform", "get_eri", "do_rmp2", "RCCD",
-           "RCCSD", "AutoRCCSD", "get_fock", "compute_pT", "CC_DEFAULTS", "gemm", "JuesError", "LibraryMissing", "default_context", "synth"]
+           "RCCSD", "AutoRCCSD", "mRCCD", "get_fock", "compute_pT", "CC_DEFAULTS", "gemm", "JuesError", "LibraryMissing", "default_context", "synth"]
 
 ERROR_NAMES = {-1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENCCL", -5: "ESTATE"}
 
@@ -627,6 +628,37 @@ class _AutoRCCSD:
 
 
 AutoRCCSD = _AutoRCCSD()
+
+
+class _mRCCD:
+    """JuES.CoupledCluster.mRCCD"""
+
+    def do_rccd(self, refWfn: Wfn, ctx: Optional[Context] = None, *, maxit: int = 40, doprint: bool = False,
+                return_T2: bool = False, _return_all: bool = False):
+        """mRCCD.do_rccd(refWfn; maxit=40, doprint=false, return_T2=false) (mRCCD.jl:37-120): RCCD from
+        zero amplitudes with the reference's DIIS (Float32 vectors), stops at ||dT2|| < 1e-7.
+        Returns the correlation energy, or (energy, T2) with return_T2."""
+        nao, o, v, Cao, Cav, eps = _wfn_args(refWfn)
+        g = refWfn.ao_eri
+        ctx = ctx or (g.ctx if isinstance(g, DeviceFourTensor) else default_context())
+        maxit = int(maxit)
+        e, its = C.c_double(), C.c_int()
+        rh, eh = np.zeros(max(maxit, 1)), np.zeros(max(maxit, 1))
+        T2 = np.empty((o, o, v, v), order="F") if (return_T2 or _return_all) else None
+        ctx._cb_shapes(o, v)
+        tail = (_p(Cao), o, _p(Cav), v, _p(eps), maxit, C.byref(e), C.byref(its), _p(rh), _p(eh), _p(T2))
+        if isinstance(g, DeviceFourTensor):
+            ctx._check(ctx._lib.jues_b200_mrccd_t4(ctx._h, g._h, *tail))
+        else:
+            g = _f(g, (nao,) * 4)
+            ctx._check(ctx._lib.jues_b200_mrccd(ctx._h, _p(g), nao, *tail))
+        if _return_all:
+            n = its.value
+            return dict(ecc=e.value, iterations=n, rms_hist=rh[:n].copy(), e_hist=eh[:n].copy(), T2=T2)
+        return (e.value, T2) if return_T2 else e.value
+
+
+mRCCD = _mRCCD()
 
 
 def compute_pT(*, T1, T2, Vvvvo, Vvooo, Vvovo, fo, fv, ctx: Optional[Context] = None) -> float:

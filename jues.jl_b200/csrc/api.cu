@@ -606,3 +606,47 @@ extern "C" int jues_b200_compute_pt(jues_ctx* ctx, const double* T1, const doubl
     *e_pt = pt_dev(ctx, in);
     JUES_API_END(ctx)
 }
+
+// ---------------------------------------------------------------------------------------------
+// mRCCD.do_rccd (DIIS)
+// ---------------------------------------------------------------------------------------------
+namespace {
+void run_mrccd(jues_ctx* ctx, GaoSource& src, const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+               const double* eps, int maxit, double* e, int* iterations, double* rms_hist, double* e_hist,
+               double* T2_out) {
+    JUES_REQUIRE(e != nullptr, "null energy output");
+    Problem P;
+    setup_problem(ctx, P, src.n, Cao, nocc, Cav, nvir, eps);
+    MrccdResult r = mrccd_dev(ctx, P, src, maxit, T2_out, ctx->amp_cb, ctx->amp_user);
+    *e = r.energy;
+    if (iterations) *iterations = r.iterations;
+    for (int k = 0; k < r.iterations; ++k) {
+        if (rms_hist) rms_hist[k] = r.rms_hist[k];
+        if (e_hist) e_hist[k] = r.e_hist[k];
+    }
+}
+}  // namespace
+
+extern "C" int jues_b200_mrccd(jues_ctx* ctx, const double* gao, int64_t nao, const double* Cao, int64_t nocc,
+                               const double* Cav, int64_t nvir, const double* eps, int maxit, double* e_ccd,
+                               int* iterations, double* rms_hist, double* e_hist, double* T2_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    Timer total(ctx, "total");
+    HostGaoHolder h;
+    make_host_gao(ctx, h, gao, nao, true);
+    run_mrccd(ctx, *h.src, Cao, nocc, Cav, nvir, eps, maxit, e_ccd, iterations, rms_hist, e_hist, T2_out);
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_mrccd_t4(jues_ctx* ctx, const jues_t4* gao, const double* Cao, int64_t nocc,
+                                  const double* Cav, int64_t nvir, const double* eps, int maxit, double* e_ccd,
+                                  int* iterations, double* rms_hist, double* e_hist, double* T2_out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    check_t4_is_gao(gao);
+    Timer total(ctx, "total");
+    T4Source holder(gao);
+    run_mrccd(ctx, *holder.src, Cao, nocc, Cav, nvir, eps, maxit, e_ccd, iterations, rms_hist, e_hist, T2_out);
+    JUES_API_END(ctx)
+}

@@ -631,4 +631,106 @@ AutoResult auto_rccsd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, const doubl
     return res;
 }
 
+// mRCCD.do_rccd (mRCCD.jl:37-120, cciter with DIIS :143-207): RCCD from ZERO amplitudes (T2_init!,
+// :239-246) with Pulay extrapolation over at most five (amplitude, error) pairs that the reference
+// stores in Float32 (:64-65,171,175).  B[n1,n2] = <e_n1|e_n2> normalised by max|B| (:188-194), the
+// coefficients solve B c = (0,...,0,-1) in Float32 (:195-198), the new amplitudes are
+// sum_k Float32(c_k) * Float32(T_k) accumulated in Float64 (:199-202).  Stops when the 2-norm of the
+// un-extrapolated change drops below 1e-7 (:106,205-206) or after maxit sweeps.
+// The sweep itself is the factorised RCCD sweep above (equal to mRCCD's GEMM chain).
+MrccdResult mrccd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, int maxit, double* T2_out,
+                      jues_b200_amp_cb cb, void* cb_user) {
+    JUES_REQUIRE(maxit >= 0, "maxit must be non-negative");
+    CC cc(ctx, P, false);
+    cc.build_integrals(gao);
+    cc.register_static();
+    cc.guess(1);
+    cc.T2.buf.zero();                                   // zeros ./ Dijab
+    const size_t n2 = (size_t)(cc.o * cc.o * cc.v * cc.v);   // even: every extent is even
+    constexpr int kMaxPairs = 5;                        // max_diis = 6 vectors, the oldest never used (:179-184)
+    struct Pair { DBuf val, err; };
+    std::vector<Pair> pairs;
+    std::vector<std::vector<float>> dots;               // dots[a][b] = Float32(<e_a|e_b>)
+    DBuf scal(ctx, 8);
+    std::vector<double> h2;
+    MrccdResult res;
+    for (int it = 0; it < maxit; ++it) {
+        double hbuf[8];
+        {
+            Timer t(ctx, "cc.iteration");
+            cc.iterate();                               // T2 = un-extrapolated new amplitudes, T2n = old ones
+            Pair p;
+            p.val.alloc(ctx, n2 / 2 + 1);
+            p.err.alloc(ctx, n2 / 2 + 1);
+            to_float32(ctx, n2, cc.T2.p(), nullptr, reinterpret_cast<float*>(p.val.p));
+            to_float32(ctx, n2, cc.T2.p(), cc.T2n.p(), reinterpret_cast<float*>(p.err.p));
+            sqdiff_async(ctx, n2, cc.T2.p(), cc.T2n.p(), scal.p);          // ||T2new - T2old||^2 in FP64 (:205)
+            pairs.push_back(std::move(p));
+            if ((int)pairs.size() > kMaxPairs) {
+                pairs.erase(pairs.begin());
+                dots.erase(dots.begin());
+                for (auto& row : dots) row.erase(row.begin());
+            }
+            const int n = (int)pairs.size();
+            for (int a = 0; a < n; ++a)
+                dot_float32_async(ctx, n2, reinterpret_cast<const float*>(pairs[a].err.p),
+                                  reinterpret_cast<const float*>(pairs[n - 1].err.p), scal.p + 1 + a);
+            JUES_CUDA(cudaMemcpyAsync(hbuf, scal.p, (size_t)(n + 1) * sizeof(double), cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+            JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (auto& row : dots) row.push_back(0.0f);
+            dots.emplace_back((size_t)n, 0.0f);
+            for (int a = 0; a < n; ++a) dots[a][n - 1] = dots[n - 1][a] = (float)hbuf[1 + a];
+            // B (n+1 x n+1, Float32), normalised, solved by Gaussian elimination with partial pivoting
+            const int m = n + 1;
+            std::vector<float> B((size_t)m * m, -1.0f), rhs((size_t)m, 0.0f);
+            B[(size_t)m * m - 1] = 0.0f;
+            float bmax = 0.0f;
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b) bmax = std::max(bmax, std::fabs(dots[a][b]));
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b) B[a + (size_t)m * b] = bmax > 0.0f ? dots[a][b] / bmax : dots[a][b];
+            rhs[m - 1] = -1.0f;
+            for (int c = 0; c < m; ++c) {
+                int piv = c;
+                for (int r = c + 1; r < m; ++r)
+                    if (std::fabs(B[r + (size_t)m * c]) > std::fabs(B[piv + (size_t)m * c])) piv = r;
+                if (piv != c) {
+                    for (int k = 0; k < m; ++k) std::swap(B[c + (size_t)m * k], B[piv + (size_t)m * k]);
+                    std::swap(rhs[c], rhs[piv]);
+                }
+                const float d = B[c + (size_t)m * c];
+                JUES_REQUIRE(d != 0.0f, "mRCCD: singular DIIS matrix");
+                for (int r = c + 1; r < m; ++r) {
+                    const float f = B[r + (size_t)m * c] / d;
+                    for (int k = c; k < m; ++k) B[r + (size_t)m * k] -= f * B[c + (size_t)m * k];
+                    rhs[r] -= f * rhs[c];
+                }
+            }
+            std::vector<float> ci((size_t)m, 0.0f);
+            for (int r = m - 1; r >= 0; --r) {
+                float acc = rhs[r];
+                for (int k = r + 1; k < m; ++k) acc -= B[r + (size_t)m * k] * ci[k];
+                ci[r] = acc / B[r + (size_t)m * r];
+            }
+            const float* vecs[8];
+            for (int a = 0; a < n; ++a) vecs[a] = reinterpret_cast<const float*>(pairs[a].val.p);
+            diis_combine(ctx, n2, n, vecs, ci.data(), cc.T2.p());
+        }
+        const double r2 = std::sqrt(hbuf[0]);
+        res.rms_hist.push_back(r2);
+        res.e_hist.push_back(cc.energy());
+        res.iterations = it + 1;
+        if (cb) {
+            h2.resize((size_t)(P.nocc * P.nocc * P.nvir * P.nvir));
+            cc.download(nullptr, h2.data());
+            cb(cb_user, it + 1, res.e_hist.back(), nullptr, h2.data());
+        }
+        if (r2 < 1e-7) break;                                                  // :106
+    }
+    res.energy = cc.energy();                                                  // :116-118
+    cc.download(nullptr, T2_out);
+    return res;
+}
+
 }  // namespace jues

@@ -48,6 +48,15 @@ AutoResult auto_rccsd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, const doubl
                           const double* fvv, const AutoOptions& opt, double* T1_out, double* T2_out,
                           jues_b200_amp_cb cb, void* cb_user);
 
+// mRCCD.do_rccd (mRCCD.jl:37-120): RCCD from zero amplitudes with the reference's Float32 DIIS.
+struct MrccdResult {
+    double energy = 0.0;
+    int iterations = 0;
+    std::vector<double> rms_hist, e_hist;   // [iterations]: ||dT||_2 before, energy after the extrapolation
+};
+MrccdResult mrccd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, int maxit, double* T2_out,
+                      jues_b200_amp_cb cb, void* cb_user);
+
 // get_fock (IntegralTransformation.jl:119-141): f = C^T h C + 2 sum_k (pq|kk) - sum_k (pk|qk), k over the
 // columns of Co.  hao (nao,nao), C (nao,nmo), Co (nao,nocc): HOST; f_out (nmo,nmo): HOST.
 void fock_dev(jues_ctx* ctx, GaoSource& gao, const double* hao, const double* C, int64_t nmo,

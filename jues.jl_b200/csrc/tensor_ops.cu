@@ -322,6 +322,38 @@ __global__ void sqdiff_kernel(const double* __restrict__ x, const double* __rest
     if (threadIdx.x == 0) partial[blockIdx.x] = r;
 }
 
+__global__ void to_float32_kernel(const double* __restrict__ x, const double* __restrict__ y, long long n,
+                                  float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = (float)(y ? x[i] - y[i] : x[i]);
+}
+
+__global__ void dot_float32_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                   double* __restrict__ partial) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        acc += (double)a[i] * (double)b[i];
+    const double r = block_reduce<256>(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+struct DiisVecs {
+    const float* v[8];
+    float c[8];
+    int n;
+};
+
+__global__ void diis_combine_kernel(DiisVecs d, long long n, double* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int q = 0; q < d.n; ++q) acc += (double)__fmul_rn(d.c[q], d.v[q][i]);   // Float32 product, no FMA
+        out[i] = acc;
+    }
+}
+
 __global__ void synth_eri_kernel(double* __restrict__ g, long long n, long long np, long long lam_lo,
                                  long long lam_count, long long sig_lo, long long sig_count,
                                  unsigned long long seed, double scale, int phys) {
@@ -577,6 +609,30 @@ void sqdiff_async(jues_ctx* ctx, size_t n, const double* x, const double* y, dou
     sqdiff_kernel<<<blocks, 256, 0, ctx->stream>>>(x, y, (long long)n, ctx->red_dev);
     AUX_LAUNCHED(ctx);
     final_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, blocks, dev_out);
+    AUX_LAUNCHED(ctx);
+}
+
+void to_float32(jues_ctx* ctx, size_t n, const double* x, const double* y, float* out32) {
+    if (!n) return;
+    to_float32_kernel<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(x, y, (long long)n, out32);
+    AUX_LAUNCHED(ctx);
+}
+
+void dot_float32_async(jues_ctx* ctx, size_t n, const float* a, const float* b, double* dev_out) {
+    int blocks = ew_grid(ctx, n, 256);
+    if (blocks > (int)ctx->red_cap - 4) blocks = (int)ctx->red_cap - 4;
+    dot_float32_kernel<<<blocks, 256, 0, ctx->stream>>>(a, b, (long long)n, ctx->red_dev);
+    AUX_LAUNCHED(ctx);
+    final_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, blocks, dev_out);
+    AUX_LAUNCHED(ctx);
+}
+
+void diis_combine(jues_ctx* ctx, size_t n, int nvec, const float* const* vecs, const float* c, double* out) {
+    JUES_REQUIRE(nvec >= 1 && nvec <= 8, "diis_combine: 1..8 vectors");
+    DiisVecs d;
+    d.n = nvec;
+    for (int q = 0; q < 8; ++q) { d.v[q] = q < nvec ? vecs[q] : nullptr; d.c[q] = q < nvec ? c[q] : 0.0f; }
+    diis_combine_kernel<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(d, (long long)n, out);
     AUX_LAUNCHED(ctx);
 }
 

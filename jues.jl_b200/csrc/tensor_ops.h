@@ -89,6 +89,15 @@ void dot_axpby(jues_ctx* ctx, size_t n, double alpha, const double* x, const dou
 // dev_out[0] = sum_k (x[k] - y[k])^2   (deterministic two-pass tree, no host synchronisation)
 void sqdiff_async(jues_ctx* ctx, size_t n, const double* x, const double* y, double* dev_out);
 
+// ---- mRCCD's DIIS keeps its vectors in Float32 (mRCCD.jl:64-65,171,175) --------------------------
+// out32[k] = float(x[k] - y[k])   (y nullable: plain conversion)
+void to_float32(jues_ctx* ctx, size_t n, const double* x, const double* y, float* out32);
+// dev_out[0] = sum_k a[k] b[k] of two Float32 vectors, accumulated in FP64 (deterministic tree)
+void dot_float32_async(jues_ctx* ctx, size_t n, const float* a, const float* b, double* dev_out);
+// out[k] = sum_{q<nvec} double(c[q] * vecs[q][k])   -- Float32 products summed in FP64 in the order q = 0,1,...
+// exactly as `tiJaB_d .+= convert(Float32,ci[num])*diis_vals_t2[num+1]` does (mRCCD.jl:200-202)
+void diis_combine(jues_ctx* ctx, size_t n, int nvec, const float* const* vecs, const float* c, double* out);
+
 // counter-based synthetic ERIs (same function as jues.jl_b200.synth.counter_eri_element)
 void synth_eri_fill(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padded, int64_t sig_lo,
                     int64_t sig_count, unsigned long long seed, double scale, bool phys = false);

@@ -12,6 +12,7 @@
 #     JuES.IntegralTransformation.get_fock(wfn; spin)              (src/Backend/IntegralTransformation.jl:119)
 #     JuES.CoupledCluster.AutoRCCSD.do_rccsd(wfn; kwargs...)       (src/CoupledCluster/AutoRCCSD.jl:193)
 #     JuES.CoupledCluster.PerturbativeTriples.compute_pT(; ...)    (src/CoupledCluster/PerturbativeTriples.jl:35)
+#     JuES.CoupledCluster.mRCCD.do_rccd(refWfn; maxit, ...)        (src/CoupledCluster/mRCCD.jl:37)
 #
 # dispatch to the device when the backend switch is :b200 -- selected with the environment
 # variable JUES_BACKEND=b200 (read at load time) or `JuESB200.set_backend(:b200)`, the twin of
@@ -276,6 +277,25 @@ function auto_rccsd(wfn; kwargs...)
     end
     n = Int(its[])
     e[], (d[:do_pT] ? ept[] : nothing), n, conv[] == 1, eh[1:n+1], rh[1:n+1]
+end
+
+function mrccd(refWfn; maxit=40, doprint=false, return_T2=false)      # mRCCD.jl:37
+    e = Ref{Float64}(0.0); its = Ref{Cint}(0)
+    o, v = refWfn.nalpha, refWfn.nvira
+    T2 = return_T2 ? Array{Float64}(undef, o, o, v, v) : C_NULL
+    g = refWfn.ao_eri
+    if g isa DeviceFourTensor
+        check(ccall(sym(:jues_b200_mrccd_t4), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Cint,
+                     Ref{Float64}, Ref{Cint}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    ctx[], g.h, refWfn.Cao, o, refWfn.Cav, v, refWfn.epsa, maxit, e, its, C_NULL, C_NULL, T2))
+    else
+        check(ccall(sym(:jues_b200_mrccd), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Cint,
+                     Ref{Float64}, Ref{Cint}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    ctx[], g, size(g, 1), refWfn.Cao, o, refWfn.Cav, v, refWfn.epsa, maxit, e, its, C_NULL, C_NULL, T2))
+    end
+    return_T2 ? (e[], T2) : e[]                                       # mRCCD.jl:115-119
 end
 
 function compute_pT(; T1::Array{Float64,2}, T2::Array{Float64,4}, Vvvvo::Array{Float64,4},

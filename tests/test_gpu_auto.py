@@ -243,3 +243,28 @@ def test_auto_rccsd_with_triples(ctx, N, o, seed, fcn):
     assert abs(got["ept"] - ref["ept"]) <= E_TOL, (got["ept"], ref["ept"])
     e, ept = jb.AutoRCCSD.do_rccsd(w, ctx=ctx, do_pT=True, fcn=fcn)
     assert e == got["ecc"] and ept == got["ept"]
+
+
+# ------------------------------------------------------------------------------------------
+# mRCCD (DIIS with Float32 vectors)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,o,seed", [(10, 3, 7), (16, 4, 2), (24, 5, 2024)])
+def test_mrccd_diis(ctx, N, o, seed):
+    """The reference keeps its DIIS vectors -- hence the extrapolated amplitudes -- in Float32
+    (mRCCD.jl:64-65,171,200-202), so parity with the CPU path is bounded by Float32 rounding of the
+    amplitudes (~6e-8 relative) and of the B matrix: energies within 1e-6 Eh, amplitudes within
+    1e-6, same number of sweeps +-1, and the converged energy equals the DIIS-free RCCD one."""
+    w, wo = canonical(N, o, seed)
+    ref = oa.do_mrccd(wo, return_all=True)
+    got = jb.mRCCD.do_rccd(w, ctx=ctx, _return_all=True)
+    assert abs(got["iterations"] - ref["iterations"]) <= 1 and got["iterations"] < 40
+    assert abs(got["ecc"] - ref["ecc"]) <= 1e-6
+    assert np.abs(got["T2"] - ref["T2"]).max() <= 1e-6
+    assert got["rms_hist"][-1] < 1e-7
+    # first sweep from zero amplitudes is the MP2 amplitudes rounded to Float32
+    assert abs(got["e_hist"][0] - orc.do_rmp2(wo)) <= 1e-6
+    assert abs(got["rms_hist"][0] - ref["rms_hist"][0]) <= 1e-12
+    assert abs(got["ecc"] - orc.do_rccd(wo, maxit=60, guess="mp2")) <= 1e-6
+    e, T2 = jb.mRCCD.do_rccd(w, ctx=ctx, return_T2=True)
+    assert e == got["ecc"] and np.array_equal(T2, got["T2"])           # deterministic
+    assert jb.mRCCD.do_rccd(w, ctx=ctx, maxit=2, _return_all=True)["iterations"] == 2
