@@ -48,13 +48,15 @@ REF_MAXIT = 40          # RCCSD.jl:36
 
 
 def flops_alg_rccsd(o, v):
-    """F_alg of SURVEY.md section 8a (factorised RCCSD sweep)."""
-    return 2 * o**2 * v**4 + 22 * o**3 * v**3 + 4 * o**4 * v**2 + 24 * o**2 * v**3 + 24 * o**3 * v**2
+    """F_alg of SURVEY.md section 8a (factorised RCCSD sweep): jues.jl_b200/flops.py."""
+    from importlib import import_module
+    return import_module("jues.jl_b200.flops").rccsd_iter_alg(o, v)
 
 
 def flops_ref_rccsd(o, v):
     """F_ref: the reference's literal sweep (Wabef built and applied, 13 ring-type terms)."""
-    return 4 * o**2 * v**4 + 4 * o * v**4 + 26 * o**3 * v**3 + 4 * o**4 * v**2 + 16 * o**2 * v**3
+    from importlib import import_module
+    return import_module("jues.jl_b200.flops").rccsd_iter_ref(o, v)
 
 
 def make_inputs(pinned: bool):

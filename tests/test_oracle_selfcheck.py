@@ -111,3 +111,18 @@ def test_counter_eri_symmetry_and_slabs():
     slab = jb.synth.counter_eri(N, seed=3, scale=0.1, sig_range=(2, 5))
     assert np.array_equal(slab, g[:, :, :, 2:5])
     assert np.abs(g).max() <= 0.1 and np.abs(g.mean()) < 0.01
+
+
+def test_flop_model_matches_the_survey_table():
+    """jues.jl_b200/flops.py against SURVEY.md section 8a (C3 column: N=120, o=20, v=100)."""
+    from importlib import import_module
+    f = import_module("jues.jl_b200.flops")
+    assert f.full_transform_flops(120) == 8 * 120**5
+    assert abs(f.tei_flops_ref(120, 20, 100, 20, 100) / 5.51e10 - 1) < 2e-3
+    assert abs(f.tei_flops_best(120, 20, 100, 20, 100) / 1.18e10 - 1) < 2e-3
+    assert abs(f.rccsd_transforms_ref(120, 20, 100) / 7.29e11 - 1) < 2e-3
+    assert abs(f.rccd_transforms_ref(120, 20, 100) / 2.99e11 - 1) < 2e-3
+    assert abs(f.rccd_iter_alg(20, 100) / 2.65e11 - 1) < 3e-3 and abs(f.rccd_iter_ref(20, 100) / 3.45e11 - 1) < 3e-3
+    assert abs(f.rccsd_iter_alg(20, 100) / 2.74e11 - 1) < 3e-3
+    assert f.ladder_flops(60, 400) == 2 * 60**2 * 400**4
+    assert f.tei_flops_best(50, 5, 45, 5, 45, streamed=True) >= f.tei_flops_best(50, 5, 45, 5, 45)
