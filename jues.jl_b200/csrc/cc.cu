@@ -597,28 +597,61 @@ AutoResult auto_rccsd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, const doubl
     report(0, Ecc);
     double dE = 1.0, rms = 1.0;
     int ite = 1;
+    // One sweep + its three scalars [E, |dT1|^2, |dT2|^2] into scalars[3*(k%2)..], copied to pinned host
+    // memory; `done[k%2]` fires when they have landed.
+    DBuf sc2(ctx, 8);
+    double* hp = ctx->red_host + 8;                    // pinned landing zone: 2 x 3 doubles
+    cudaEvent_t done[2];
+    JUES_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    JUES_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    auto enqueue = [&](int k) {
+        const double f0 = ctx->stats.gemm_flops;
+        Timer t(ctx, "cc.iteration");
+        cc.iterate();                       // afterwards T1/T2 are the new, T1n/T2n the old amplitudes
+        double* s3 = sc2.p + 3 * (k & 1);
+        sqdiff_async(ctx, n1, cc.T1.p(), cc.T1n.p(), s3 + 1);                 // :174-175
+        sqdiff_async(ctx, n2, cc.T2.p(), cc.T2n.p(), s3 + 2);
+        cc.energy_async(s3);
+        dot_axpby(ctx, n1, 2.0, cc.fov.p(), cc.T1.p(), 1.0, s3);
+        t.stop();
+        ctx->timings.emplace_back("cc.iteration.gflop", (float)((ctx->stats.gemm_flops - f0) * 1e-9));
+        JUES_CUDA(cudaMemcpyAsync(hp + 3 * (k & 1), s3, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        JUES_CUDA(cudaEventRecord(done[k & 1], ctx->stream));
+    };
+    // The reference's loop (:270-285) decides after every sweep.  Without a per-sweep amplitude
+    // callback the NEXT sweep is enqueued before the host waits for the scalars of the current one,
+    // so the launch queue never drains; when the current sweep turns out to be the last, the
+    // speculative one is discarded (the amplitudes it started from are still in T1n/T2n).
+    const bool speculate = (cb == nullptr);
+    bool in_flight = false;                 // sweep `ite` already enqueued
     while (std::fabs(dE) > opt.e_conv || rms > opt.max_rms) {                 // :270
         if (ite > opt.max_iter) break;                                        // :271-274
-        {
-            const double f0 = ctx->stats.gemm_flops;
-            Timer t(ctx, "cc.iteration");
-            cc.iterate();                       // afterwards T1/T2 are the new, T1n/T2n the old amplitudes
-            sqdiff_async(ctx, n1, cc.T1.p(), cc.T1n.p(), scal.p + 1);         // :174-175
-            sqdiff_async(ctx, n2, cc.T2.p(), cc.T2n.p(), scal.p + 2);
-            energy();
-            t.stop();
-            ctx->timings.emplace_back("cc.iteration.gflop", (float)((ctx->stats.gemm_flops - f0) * 1e-9));
+        if (!in_flight) enqueue(ite);
+        in_flight = false;
+        if (speculate && ite + 1 <= opt.max_iter) {
+            enqueue(ite + 1);
+            in_flight = true;
         }
-        read(3);
-        rms = std::max(std::sqrt(h[1]) / len1, std::sqrt(h[2]) / len2);       // :278
+        JUES_CUDA(cudaEventSynchronize(done[ite & 1]));
+        const double* hk = hp + 3 * (ite & 1);
+        rms = std::max(std::sqrt(hk[1]) / len1, std::sqrt(hk[2]) / len2);     // :278
         const double oldE = Ecc;
-        Ecc = h[0];
+        Ecc = hk[0];
         dE = Ecc - oldE;
         res.e_hist.push_back(Ecc);
         res.rms_hist.push_back(rms);
         report(ite, Ecc);
         ++ite;
     }
+    if (in_flight) {
+        // discard the speculative sweep: swap the previous amplitudes back
+        std::swap(cc.T2.buf, cc.T2n.buf); std::swap(cc.T2.t, cc.T2n.t);
+        std::swap(cc.T1.buf, cc.T1n.buf); std::swap(cc.T1.t, cc.T1n.t);
+        ctx->timings.emplace_back("cc.speculative_sweeps", 1.0f);
+    }
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
     res.iterations = ite - 1;
     res.converged = std::fabs(dE) < opt.e_conv && rms < opt.max_rms;          // :288
     res.ecc = Ecc;

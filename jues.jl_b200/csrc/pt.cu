@@ -183,12 +183,15 @@ double pt_dev(jues_ctx* ctx, const PtInputs& in) {
             for (int64_t k0 = 0; k0 <= j; k0 += kbmax) {
                 const int64_t kb = std::min(kbmax, j + 1 - k0);
                 const int64_t fam = kb * v3;   // one family of X blocks
+                TraceTimer* tg = new TraceTimer(ctx, "pt.gemm");
                 x_blocks(ctx, in, i, 0, j, 0, k0, 1, kb, X.p);             // X(i,j,k)
                 x_blocks(ctx, in, i, 0, k0, 1, j, 0, kb, X.p + fam);       // X(i,k,j)
                 x_blocks(ctx, in, k0, 1, i, 0, j, 0, kb, X.p + 2 * fam);   // X(k,i,j)
                 x_blocks(ctx, in, k0, 1, j, 0, i, 0, kb, X.p + 3 * fam);   // X(k,j,i)
                 x_blocks(ctx, in, j, 0, k0, 1, i, 0, kb, X.p + 4 * fam);   // X(j,k,i)
                 x_blocks(ctx, in, j, 0, i, 0, k0, 1, kb, X.p + 5 * fam);   // X(j,i,k)
+                delete tg;
+                TraceTimer ta(ctx, "pt.assemble+energy");
                 const int grid = ew_grid(ctx, (size_t)fam, 256);
                 pt_assemble_kernel<<<grid, 256, 0, ctx->stream>>>(X.p, in.Vv, in.t1, W.p, V.p, (int)o, (int)v,
                                                                   (int)i, (int)j, (int)k0, (int)kb);

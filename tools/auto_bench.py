@@ -60,6 +60,9 @@ def main():
              "cc.transform_ms": ph.get("cc.transform"), "fock.build_ms": ph.get("fock.build"),
              "cc.triples_ms": ph.get("cc.triples"), "total_ms": ph.get("total"),
              "launches": [c["gemm_launches"], c["aux_launches"]]}
+        tr = {k: round(float(sum(vv)), 3) for k, vv in ph.items() if k.startswith(("pt.", "cc.part", "cc.comm", "tei."))}
+        if tr:
+            d["trace_ms_sum"] = tr          # JUES_B200_TRACE=1: fine-grained CUDA-event timers, summed
         if d["sweep_exec_tflops"]:
             d["sweep_frac_of_fp64_peak"] = d["sweep_exec_tflops"] / peak
         if ph.get("cc.triples"):
