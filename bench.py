@@ -414,6 +414,10 @@ def gpu_arm(args, rank, world):
                 "what": "jues_b200_rccsd(host gao, Cao, Cav, eps, maxit=40): H2D + transform + 40 sweeps + energies D2H"},
         "gpu_launches": int(round(launches_step)),
         "ms_each_step_rank0": [round(x, 3) for x in it_ms],
+        # host clock (ms since the first sweep was issued) at which each sweep had been handed to the
+        # driver, and how many sweeps were replayed from a CUDA graph: the launching thread runs ahead
+        "host_issue_ms_rank0": [round(ms, 3) for k, ms in ph if k == "cc.iteration.host_ms"],
+        "graph_replayed_sweeps": int(sum(ms for k, ms in ph if k == "cc.graph_launches")),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks,

@@ -568,25 +568,26 @@ extern "C" int jues_b200_compute_pt(jues_ctx* ctx, const double* T1, const doubl
     JUES_REQUIRE(nocc > 0 && nvir > 0, "nocc and nvir must be positive");
     Timer total(ctx, "total");
     const int64_t o = round_up(nocc, 2), v = round_up(nvir, 2);
-    DTen t1, t2, a, b, c;
-    DTen OAp(ctx, v, v, o, v), Ov(ctx, o, v, o, o), Vv(ctx, v, v, o, o), Tq(ctx, v, v, o, o);
+    const int64_t K = v + o;
+    DTen t1, Acat(ctx, v, v, o, K), Bq(ctx, v, o, K, o), Br(ctx, v, o, K, o), Vv(ctx, v, v, o, o);
     {
         Timer t(ctx, "pt.upload");
+        DTen t2, a, b, c, OAp(ctx, v, v, o, v), ooov(ctx, o, o, o, v);
         upload_padded_matrix(ctx, t1.buf, T1, nocc, nvir, o, v);
         t1.t = Ten(t1.buf.p, o, v);
         const int64_t d2[4] = {nocc, nocc, nvir, nvir}, p2[4] = {o, o, v, v};
         upload_padded_t4(ctx, t2, T2, d2, p2);
-        permute_axpby(ctx, 1.0, t2, "ijab", 0.0, Tq, "abji");
         const int64_t da[4] = {nvir, nvir, nvir, nocc}, pa[4] = {v, v, v, o};
         upload_padded_t4(ctx, a, Vvvvo, da, pa);                       // Vvvvo[b,d,a,p] = <pd|ab>
         permute_axpby(ctx, 1.0, a, "bdap", 0.0, OAp, "abpd");
         a.release();
         const int64_t db[4] = {nvir, nocc, nocc, nocc}, pb[4] = {v, o, o, o};
-        upload_padded_t4(ctx, b, Vvooo, db, pb);                       // Vvooo[c,r,q,l] = <qr|lc>
-        permute_axpby(ctx, 1.0, b, "crql", 0.0, Ov, "lcqr");
+        upload_padded_t4(ctx, b, Vvooo, db, pb);                       // Vvooo[c,r,q,l] = <qr|lc> = ooov[q,r,l,c]
+        permute_axpby(ctx, 1.0, b, "crql", 0.0, ooov, "qrlc");
         const int64_t dc[4] = {nvir, nocc, nvir, nocc}, pc[4] = {v, o, v, o};
         upload_padded_t4(ctx, c, Vvovo, dc, pc);                       // Vvovo[a,i,b,j] = <ij|ab>
         permute_axpby(ctx, 1.0, c, "aibj", 0.0, Vv, "abij");
+        pt_build_operands(ctx, o, v, OAp.p(), t2.p(), ooov.p(), Acat.p(), Bq.p(), Br.p());
     }
     double emin = fo[0], emax = fv[0];
     for (int64_t k = 0; k < nocc; ++k) emin = std::min(emin, fo[k]);
@@ -600,7 +601,7 @@ extern "C" int jues_b200_compute_pt(jues_ctx* ctx, const double* T1, const doubl
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     PtInputs in;
     in.o = o; in.v = v; in.nocc = nocc;
-    in.OAp = OAp.p(); in.Ov = Ov.p(); in.Vv = Vv.p(); in.Tq = Tq.p(); in.t1 = t1.p();
+    in.Acat = Acat.p(); in.Bq = Bq.p(); in.Br = Br.p(); in.Vv = Vv.p(); in.t1 = t1.p();
     in.eo = eod.p; in.ev = evd.p;
     Timer t(ctx, "pt.energy");
     *e_pt = pt_dev(ctx, in);

@@ -278,7 +278,12 @@ struct CC {
         for (DTen* t : {&V, &J, &oooo, &ooov, &Vt, &oovo, &ooov_t, &OA, &OB})
             if (t->p()) pcache.add(t->t, false);
     }
-    ~CC() { ctx->perm_cache = nullptr; pcache.clear(); }
+    ~CC() {
+        for (auto& g : graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        ctx->perm_cache = nullptr;
+        pcache.clear();
+    }
 
     double energy() { return cc_energy(ctx, V.p(), T2.p(), singles ? T1.p() : nullptr, o, v); }
     void energy_async(double* dev_out) { cc_energy_async(ctx, V.p(), T2.p(), singles ? T1.p() : nullptr, o, v, dev_out); }
@@ -427,8 +432,79 @@ struct CC {
         residual_finish(ctx, V_S.p, Lpp.p(), Lhh.p(), H.p, Hfull.p(), Tn_S.p, P.eo.p, P.ev.p, o, v, b0, vs);
         { TraceTimer tt(ctx, "cc.comm.gatherT2"); all_gather_inplace(ctx, T2n.p(), ns); }
         pcache.end_sweep();
+        swap_amplitudes();
+    }
+
+    void swap_amplitudes() {
         std::swap(T2.buf, T2n.buf); std::swap(T2.t, T2n.t);
         if (singles) { std::swap(T1.buf, T1n.buf); std::swap(T1.t, T1n.t); }
+    }
+
+    // ---- one sweep, replayed from a CUDA graph once the launch sequence is warm ---------------------
+    // A sweep is ~100 kernel launches and ~300 stream-ordered allocations; issued one by one the GPU
+    // idles whenever the launching thread is descheduled for longer than the queue it has built up
+    // (measured on shared hosts: single sweeps of 9 ms stretched to 15-240 ms).  After two eager sweeps
+    // (every lazily built operand copy, kernel attribute and pool block exists) the sweep is captured
+    // once per amplitude-buffer parity (T2 -> T2n and back) and replayed with one cudaGraphLaunch, so
+    // the host can run arbitrarily far ahead.  Capture failures fall back to eager launches.
+    struct SweepGraph { cudaGraphExec_t exec = nullptr; Stats delta; };
+    SweepGraph graphs[2];
+    const double* t2_even = nullptr;
+    int eager_sweeps = 0;
+    bool graph_ok = true;
+
+    void sweep() {
+        static const bool off = getenv("JUES_B200_NO_GRAPH") != nullptr || getenv("JUES_B200_TRACE") != nullptr;
+        if (off || !graph_ok || ctx->nranks != 1 || eager_sweeps < 2) {
+            iterate();
+            ++eager_sweeps;
+            return;
+        }
+        if (!t2_even) t2_even = T2.p();
+        SweepGraph& g = graphs[T2.p() == t2_even ? 0 : 1];
+        if (g.exec) {
+            swap_amplitudes();              // what iterate() does on the host side
+        } else {
+            const Stats before = ctx->stats;
+            cudaGraph_t graph = nullptr;
+            bool captured = false;
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                bool threw = false;
+                try {
+                    iterate();
+                } catch (const Error&) {
+                    threw = true;
+                }
+                const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+                if (!threw && e == cudaSuccess && graph &&
+                    cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess)
+                    captured = true;
+                if (graph) cudaGraphDestroy(graph);
+                if (!captured) {
+                    cudaGetLastError();
+                    g.exec = nullptr;
+                    if (!threw) swap_amplitudes();   // undo the host-side swap of the sweep that never ran
+                    pcache.end_sweep();
+                }
+            } else {
+                cudaGetLastError();
+            }
+            if (!captured) {
+                graph_ok = false;
+                ctx->stats = before;
+                iterate();
+                return;
+            }
+            g.delta.gemm_flops = ctx->stats.gemm_flops - before.gemm_flops;
+            g.delta.gemm_launches = ctx->stats.gemm_launches - before.gemm_launches;
+            g.delta.aux_launches = ctx->stats.aux_launches - before.aux_launches;
+            ctx->stats = before;
+        }
+        JUES_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+        ctx->stats.gemm_flops += g.delta.gemm_flops;
+        ctx->stats.gemm_launches += g.delta.gemm_launches;
+        ctx->stats.aux_launches += g.delta.aux_launches;
+        ctx->stats.graph_launches += 1;
     }
 
     // Off-diagonal Fock blocks (host, unpadded, diagonals already removed by the caller):
@@ -456,28 +532,27 @@ struct CC {
     double triples() {
         JUES_REQUIRE(singles, "(T) needs the RCCSD integral classes");
         pcache.clear();
-        W4.release(); OB.release(); J.release(); oooo.release(); Vt.release(); oovo.release(); ooov_t.release();
+        OB.release(); J.release(); oooo.release(); Vt.release(); oovo.release(); ooov_t.release();
         T2n.release();
-        DTen OAfull;
-        const double* OAp = OA.p();          // OA[e,f,m,b] = <ef|mb> = <mb|ef>: already OAp[a,b,p,d]
-        if (ctx->nranks > 1) {
-            const size_t cnt = (size_t)(v * v * o * vs);
-            OAfull.alloc(ctx, v, v, o, v);
-            JUES_CUDA(cudaMemcpyAsync(OAfull.p() + (size_t)ctx->rank * cnt, OA.p(), cnt * sizeof(double),
-                                      cudaMemcpyDeviceToDevice, ctx->stream));
-            all_gather_inplace(ctx, OAfull.p(), cnt);
-            OA.release();
-            OAp = OAfull.p();
-        }
-        DTen Ov(ctx, o, v, o, o), Vv(ctx, v, v, o, o), Tq(ctx, v, v, o, o);
-        permute_axpby(ctx, 1.0, ooov, "qrlc", 0.0, Ov, "lcqr");
+        DBuf scratch = std::move(W4.buf);     // the <vv|vv> slab becomes the triples' work space
+        const int64_t K = v + o;
+        TraceTimer* tp = new TraceTimer(ctx, "pt.prepare");
+        DTen Acat(ctx, v, v, o, K), Bq(ctx, v, o, K, o), Br(ctx, v, o, K, o), Vv(ctx, v, v, o, o);
+        // OA[e,f,m,b] = <ef|mb> = <mb|ef> is the kap < v block of Acat[a,b,p,kap]; with several ranks each
+        // holds the slab b in S_r of it, which is all-gathered in place
+        const size_t cnt = (size_t)(v * v * o * vs);
+        JUES_CUDA(cudaMemcpyAsync(Acat.p() + (size_t)ctx->rank * cnt, OA.p(), cnt * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        all_gather_inplace(ctx, Acat.p(), cnt);
+        OA.release();
+        pt_build_operands(ctx, o, v, nullptr, T2.p(), ooov.p(), Acat.p(), Bq.p(), Br.p());
         permute_axpby(ctx, 1.0, V, "ijab", 0.0, Vv, "abij");
-        permute_axpby(ctx, 1.0, T2, "ijab", 0.0, Tq, "abji");
+        delete tp;
         PtInputs in;
         in.o = o; in.v = v; in.nocc = P.nocc;
-        in.OAp = OAp; in.Ov = Ov.p(); in.Vv = Vv.p(); in.Tq = Tq.p(); in.t1 = T1.p();
+        in.Acat = Acat.p(); in.Bq = Bq.p(); in.Br = Br.p(); in.Vv = Vv.p(); in.t1 = T1.p();
         in.eo = P.eo.p; in.ev = P.ev.p;
-        return pt_dev(ctx, in);
+        return pt_dev(ctx, in, scratch.p, scratch.n);
     }
 
     // host copies in the caller's (unpadded) layout
@@ -523,6 +598,7 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
     // queue stays full across sweeps.
     DBuf e_dev(ctx, (size_t)maxit + 1);
     cc.energy_async(e_dev.p);
+    const auto host_t0 = std::chrono::steady_clock::now();
     if (cb) {
         res.e_hist[0] = cc.energy();
         report(0, res.e_hist[0]);
@@ -533,11 +609,15 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
             // (RCCSD.jl:104)
             const double f0 = ctx->stats.gemm_flops;
             Timer t(ctx, "cc.iteration");
-            cc.iterate();
+            cc.sweep();
             cc.energy_async(e_dev.p + it);
             t.stop();
             // FP64 flops this rank's GEMM launches executed in the sweep (reported as a pseudo-phase)
             ctx->timings.emplace_back("cc.iteration.gflop", (float)((ctx->stats.gemm_flops - f0) * 1e-9));
+            // host clock when this sweep had been handed to the driver (diagnostic: how far the launching
+            // thread runs ahead of the GPU)
+            ctx->timings.emplace_back("cc.iteration.host_ms",
+                (float)(std::chrono::duration<double>(std::chrono::steady_clock::now() - host_t0).count() * 1e3));
         }
         if (cb) {
             res.e_hist[it] = cc.energy();
@@ -548,6 +628,7 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
                               cudaMemcpyDeviceToHost, ctx->stream));
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     res.energy = res.e_hist[maxit];
+    ctx->timings.emplace_back("cc.graph_launches", (float)ctx->stats.graph_launches);
     cc.download(singles ? T1_out : nullptr, T2_out);
     return res;
 }
@@ -607,7 +688,7 @@ AutoResult auto_rccsd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, const doubl
     auto enqueue = [&](int k) {
         const double f0 = ctx->stats.gemm_flops;
         Timer t(ctx, "cc.iteration");
-        cc.iterate();                       // afterwards T1/T2 are the new, T1n/T2n the old amplitudes
+        cc.sweep();                         // afterwards T1/T2 are the new, T1n/T2n the old amplitudes
         double* s3 = sc2.p + 3 * (k & 1);
         sqdiff_async(ctx, n1, cc.T1.p(), cc.T1n.p(), s3 + 1);                 // :174-175
         sqdiff_async(ctx, n2, cc.T2.p(), cc.T2n.p(), s3 + 2);
@@ -652,6 +733,7 @@ AutoResult auto_rccsd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, const doubl
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaEventDestroy(done[0]);
     cudaEventDestroy(done[1]);
+    ctx->timings.emplace_back("cc.graph_launches", (float)ctx->stats.graph_launches);
     res.iterations = ite - 1;
     res.converged = std::fabs(dE) < opt.e_conv && rms < opt.max_rms;          // :288
     res.ecc = Ecc;

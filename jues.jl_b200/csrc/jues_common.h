@@ -61,6 +61,7 @@ struct Stats {
     double gemm_flops = 0;       // 2*M*N*K*batch summed over launches (padded dims)
     long long gemm_launches = 0;
     long long aux_launches = 0;  // permute / elementwise / reduction kernels
+    long long graph_launches = 0; // sweeps replayed from a CUDA graph (their kernels are counted above)
     long long collectives = 0;   // NCCL calls
     double collective_bytes = 0; // bytes received per rank in collectives
     void reset() { *this = Stats(); }

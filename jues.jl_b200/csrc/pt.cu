@@ -7,13 +7,14 @@
 // with 12 small @tensoropt contractions, then a scalar a >= b >= c loop nest (:117-131).
 //
 // Here (tests/pt_model.py is the numpy statement of the same algorithm):
-//   * one "X block" per ordered triple (p,q,r):
-//         X(p,q,r)[(a,b),c] = sum_d OAp[(a,b),p,d] Tq[c,d,q,r] - sum_l Tq[(a,b),l,p] Ov[l,c,q,r]
-//     = two launches of the TMA + DMMA GEMM (M = v^2, N = v, K = v resp. o) with NO operand
-//     permutation: the layouts OAp[a,b,p,d], Tq[a,b,j,i], Ov[l,c,q,r] make every operand a strided
-//     matrix;
-//   * for a fixed pair (i,j) the six blocks of ALL k <= j are produced by 12 batched launches
-//     (the batch index walks p, q or r with a constant stride);
+//   * one "X block" per ordered triple (p,q,r), with the two contractions concatenated along K = v + o:
+//         X(p,q,r)[(a,b),c] = sum_kap Acat[(a,b),p,kap] B[c,kap,q,r]
+//         Acat = [ <p d|ab> | -T2[p,l,a,b] ],   B = [ T2[r,q,c,d] | <qr|lc> ]
+//     = ONE launch of the TMA + DMMA GEMM with NO operand permutation per block: the layouts
+//     Acat[a,b,p,kap], Bq[c,q,kap,r], Br[c,r,kap,q] (built once) make every operand a strided matrix;
+//   * for a fixed pair (i,j) the six blocks of ALL k <= j are produced by 6 launches: consecutive q
+//     (or r) are consecutive rows of Bq (Br), so N = v*nb; consecutive p are consecutive rows of Acat,
+//     so M = v^2*nb;
 //   * one kernel assembles W and V from the six blocks (index permutations + rank-1 terms), a second
 //     one evaluates the energy expression on a >= b >= c and reduces it deterministically
 //     (block tree -> one slot per batch; the slots are summed in a fixed order at the end).
@@ -123,55 +124,79 @@ __global__ void pt_slot_reduce_kernel(const double* __restrict__ partial, int n,
 }
 
 // The X blocks of `nb` consecutive triples: (p,q,r) = (p0 + ps*n, q0 + qs*n, r0 + rs*n), n < nb,
-// exactly one of ps, qs, rs being 1.
-//   qs or rs == 1:  out[n][(a,b),c]   (batched launches: the B operands walk q or r)
-//   ps == 1:        out[(a,b),n,c]    (the rows (a,b,p) of OAp are contiguous in p, so the first
-//                                      GEMM is ONE launch with M = v^2 nb; the second is batched into
-//                                      the same layout)
+// exactly one of ps, qs, rs being 1.  One GEMM, K = v + o.
+//   qs or rs == 1:  out[(a,b),(c,n)] = out[n][(a,b),c]   (N = v*nb: rows (c,q) of Bq resp. (c,r) of Br)
+//   ps == 1:        out[(a,b,n),c]                        (M = v^2*nb: rows (a,b,p) of Acat)
 void x_blocks(jues_ctx* ctx, const PtInputs& in, int64_t p0, int ps, int64_t q0, int qs, int64_t r0, int rs,
               int64_t nb, double* out) {
-    const int64_t o = in.o, v = in.v, v2 = v * v;
+    const int64_t o = in.o, v = in.v, v2 = v * v, K = v + o;
     GemmCall g;
-    g.N = v;
-    g.C = out;
-    // sum_d OAp[(a,b),p,d] Tq[c,d,q,r]
-    g.K = v;
-    g.transA = false; g.A = in.OAp + p0 * v2; g.lda = v2 * o;
-    g.transB = true;  g.B = in.Tq + v2 * (q0 + o * r0); g.ldb = v;
+    g.K = K;
+    g.transA = false; g.A = in.Acat + p0 * v2; g.lda = v2 * o;
+    g.transB = true;  g.ldb = v * o;
+    // Bq[c,q,kap,r] / Br[c,r,kap,q]: the matrix [c (and the walked index), kap] of a fixed (q,r)
+    g.B = rs ? in.Br + v * r0 + v * o * K * q0 : in.Bq + v * q0 + v * o * K * r0;
+    g.M = ps ? v2 * nb : v2;
+    g.N = ps ? v : v * nb;
+    g.C = out; g.ldc = g.M;
     g.alpha = 1.0; g.beta = 0.0;
-    if (ps) {
-        g.M = v2 * nb; g.batch = 1; g.ldc = v2 * nb;
-    } else {
-        g.M = v2; g.batch = nb; g.strideA = 0; g.strideB = v2 * (qs + o * rs);
-        g.ldc = v2; g.strideC = v2 * v;
-    }
-    dgemm(ctx, g);
-    // - sum_l Tq[(a,b),l,p] Ov[l,c,q,r]
-    g.K = o;
-    g.M = v2; g.batch = nb;
-    g.transA = false; g.A = in.Tq + v2 * o * p0; g.lda = v2; g.strideA = ps ? v2 * o : 0;
-    g.transB = false; g.B = in.Ov + o * v * (q0 + o * r0); g.ldb = o; g.strideB = o * v * (qs + o * rs);
-    if (ps) { g.ldc = v2 * nb; g.strideC = v2; }
-    g.alpha = -1.0; g.beta = 1.0;
     dgemm(ctx, g);
 }
 
 }  // namespace
 
-double pt_dev(jues_ctx* ctx, const PtInputs& in) {
+void pt_build_operands(jues_ctx* ctx, int64_t o, int64_t v, const double* OAp, const double* T2,
+                       const double* ooov, double* acat, double* bq, double* br) {
+    const int64_t K = v + o;
+    const Ten T(const_cast<double*>(T2), o, o, v, v), O3(const_cast<double*>(ooov), o, o, o, v);
+    // Acat[a,b,p,kap]: kap < v is OAp itself (kap is the slowest index: one contiguous block)
+    if (OAp)
+        JUES_CUDA(cudaMemcpyAsync(acat, OAp, (size_t)(v * v * o * v) * sizeof(double), cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+    permute_axpby(ctx, -1.0, T, "plab", 0.0, Ten(acat + v * v * o * v, v, v, o, o), "abpl");
+    // Bq[c,q,kap,r] and Br[c,r,kap,q]: permute into dense temporaries, then place the two kap ranges
+    const int64_t ddq[4] = {v, o, K, o};
+    DTen t1(ctx, v, o, v, o), t2(ctx, v, o, o, o);
+    const int64_t e1[4] = {v, o, v, o}, e2[4] = {v, o, o, o};
+    permute_axpby(ctx, 1.0, T, "rqck", 0.0, t1, "cqkr");
+    block_copy(ctx, t1.p(), e1, bq, ddq, e1);
+    permute_axpby(ctx, 1.0, O3, "qrlc", 0.0, t2, "cqlr");
+    block_copy(ctx, t2.p(), e2, bq + v * o * v, ddq, e2);
+    permute_axpby(ctx, 1.0, T, "rqck", 0.0, t1, "crkq");
+    block_copy(ctx, t1.p(), e1, br, ddq, e1);
+    permute_axpby(ctx, 1.0, O3, "qrlc", 0.0, t2, "crlq");
+    block_copy(ctx, t2.p(), e2, br + v * o * v, ddq, e2);
+}
+
+double pt_dev(jues_ctx* ctx, const PtInputs& in, double* scratch, size_t scratch_elems) {
     const int64_t o = in.o, v = in.v, nocc = in.nocc;
     JUES_REQUIRE(o > 0 && v > 0 && nocc > 0 && nocc <= o, "(T): bad extents");
     JUES_REQUIRE((o & 1) == 0 && (v & 1) == 0, "(T): internal extents must be even");
-    JUES_REQUIRE(in.OAp && in.Ov && in.Vv && in.Tq && in.t1 && in.eo && in.ev, "(T): null input");
+    JUES_REQUIRE(in.Acat && in.Bq && in.Br && in.Vv && in.t1 && in.eo && in.ev, "(T): null input");
     const int64_t v3 = v * v * v;
     // batch as many k as memory allows: 8 v^3-sized arrays per triple (6 X blocks, W, V)
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    free_b += ctx->big_cached_bytes;
-    int64_t kbmax = (int64_t)(0.6 * (double)free_b / (8.0 * 8.0 * (double)v3));
-    kbmax = std::max<int64_t>(1, std::min<int64_t>(kbmax, nocc));
+    int64_t kbmax = 0;
+    DBuf work;
+    double* base = nullptr;
+    const int64_t ks = (int64_t)(scratch_elems / (size_t)(8 * v3));
+    if (scratch && ks >= std::min<int64_t>(nocc, 4)) {
+        kbmax = std::min<int64_t>(ks, nocc);
+        base = scratch;
+    } else {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        free_b += ctx->big_cached_bytes;
+        kbmax = (int64_t)(0.6 * (double)free_b / (8.0 * 8.0 * (double)v3));
+        kbmax = std::max<int64_t>(1, std::min<int64_t>(kbmax, nocc));
+    }
     if (getenv("JUES_B200_PT_KB")) kbmax = std::max(1, atoi(getenv("JUES_B200_PT_KB")));   // testing hook
-    DBuf X(ctx, (size_t)(6 * kbmax * v3)), W(ctx, (size_t)(kbmax * v3)), V(ctx, (size_t)(kbmax * v3));
+    if (!base) {
+        TraceTimer tal(ctx, "pt.alloc");
+        work.alloc(ctx, (size_t)(8 * kbmax * v3));
+        base = work.p;
+    }
+    struct View { double* p; };
+    const View X{base}, W{base + 6 * kbmax * v3}, V{base + 7 * kbmax * v3};
     const int64_t nchunk_max = (nocc + kbmax - 1) / kbmax;
     const int64_t nslots = nocc * (nocc + 1) / 2 * nchunk_max;
     DBuf slots(ctx, (size_t)nslots + 1);

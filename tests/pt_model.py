@@ -5,16 +5,20 @@ indexed in the same letter order), same GEMM operands, same batching over the th
 index, so that every index convention of the device code is checked on the CPU against the
 literal oracle (oracle/jues_oracle_auto.compute_pT, PerturbativeTriples.jl:35-138).
 
-Device tensors:
-    OAp[a,b,p,d] = <pd|ab> = ovvv[p,d,a,b]   (the CC driver's OA[e,f,m,b] = <ef|mb> is this array)
-    Ov[l,c,q,r]  = <qr|lc> = ooov[q,r,l,c]
-    Vv[a,b,i,j]  = <ij|ab> = oovv[i,j,a,b]
-    Tq[a,b,j,i]  = T2[i,j,a,b]
-One "X" block per ordered occupied triple (p,q,r):
-    X(p,q,r)[a,b,c] = sum_d OAp[a,b,p,d] Tq[c,d,q,r]  -  sum_l Tq[a,b,l,p] Ov[l,c,q,r]
-(two GEMMs, M = v^2, N = v, K = v resp. o) and
+Device tensors (K = v + o; see jues.jl_b200/csrc/pt.h):
+    Acat[a,b,p,kap]:  kap <  v: <p kap|ab> = ovvv[p,kap,a,b]     kap >= v: -T2[p,l,a,b], l = kap - v
+    Bq[c,q,kap,r]:    kap <  v: T2[r,q,c,kap]                     kap >= v: <qr|lc> = ooov[q,r,l,c]
+    Br[c,r,kap,q]:    the same numbers, q and r exchanged in the layout
+    Vv[a,b,i,j] = <ij|ab>
+One "X" block per ordered occupied triple (p,q,r) -- ONE GEMM, the contractions over d and l
+concatenated along K:
+    X(p,q,r)[(a,b),c] = sum_kap Acat[(a,b),p,kap] B[c,kap,(q,r)]
+and
     W_ijk[a,b,c] = X(i,j,k)[a,b,c] + X(i,k,j)[a,c,b] + X(k,i,j)[c,a,b]
                  + X(k,j,i)[c,b,a] + X(j,k,i)[b,c,a] + X(j,i,k)[b,a,c]        (:96-101)
+The blocks of consecutive k come out of one launch: rows (c,q) of Bq / (c,r) of Br give N = v*nb,
+rows (a,b,p) of Acat give M = v^2*nb (x_blocks below mirrors pt.cu's pointer arithmetic on flat
+column-major buffers).
 """
 import math
 
@@ -22,19 +26,42 @@ import numpy as np
 
 
 def device_tensors(T1, T2, ovvv, ooov, oovv):
-    return dict(OAp=np.ascontiguousarray(ovvv.transpose(2, 3, 0, 1)),
-                Ov=np.ascontiguousarray(ooov.transpose(2, 3, 0, 1)),
-                Vv=np.ascontiguousarray(oovv.transpose(2, 3, 0, 1)),
-                Tq=np.ascontiguousarray(T2.transpose(2, 3, 1, 0)), t=T1)
+    o, v = T1.shape
+    K = v + o
+    Acat = np.zeros((v, v, o, K))
+    Acat[:, :, :, :v] = ovvv.transpose(2, 3, 0, 1)               # [a,b,p,d] = ovvv[p,d,a,b]
+    Acat[:, :, :, v:] = -T2.transpose(2, 3, 0, 1)                 # [a,b,p,l] = -T2[p,l,a,b]
+    Bq = np.zeros((v, o, K, o))
+    Bq[:, :, :v, :] = T2.transpose(2, 1, 3, 0)                    # [c,q,d,r] = T2[r,q,c,d]
+    Bq[:, :, v:, :] = ooov.transpose(3, 0, 2, 1)                  # [c,q,l,r] = ooov[q,r,l,c]
+    Br = np.ascontiguousarray(Bq.transpose(0, 3, 2, 1))           # [c,r,kap,q]
+    F = lambda x: np.asfortranarray(x).ravel(order="F")           # flat column-major device buffers
+    return dict(o=o, v=v, Acat=F(Acat), Bq=F(Bq), Br=F(Br),
+                Vv=np.ascontiguousarray(oovv.transpose(2, 3, 0, 1)), t=T1)
+
+
+def x_blocks(Dv, p0, ps, q0, qs, r0, rs, nb):
+    """pt.cu: x_blocks -- one GEMM on strided views of the flat buffers.  Returns the nb blocks as
+    an array [n][a,b,c]."""
+    o, v = Dv["o"], Dv["v"]
+    v2, K = v * v, v + o
+    M = v2 * nb if ps else v2
+    N = v if ps else v * nb
+    A0 = p0 * v2
+    lda = v2 * o
+    A = np.array([[Dv["Acat"][A0 + m + lda * k] for k in range(K)] for m in range(M)])
+    B0 = (v * r0 + v * o * K * q0) if rs else (v * q0 + v * o * K * r0)
+    Bb = Dv["Br"] if rs else Dv["Bq"]
+    ldb = v * o
+    B = np.array([[Bb[B0 + n + ldb * k] for k in range(K)] for n in range(N)])
+    C = A @ B.T                                                    # (M, N), column-major out[m + M*n]
+    if ps:
+        return C.reshape(v, v, nb, v, order="F").transpose(2, 0, 1, 3)   # out[(a,b,n),c]
+    return C.reshape(v, v, v, nb, order="F").transpose(3, 0, 1, 2)       # out[(a,b),(c,n)]
 
 
 def X_block(Dv, p, q, r):
-    v = Dv["Tq"].shape[0]
-    A1 = Dv["OAp"][:, :, p, :].reshape(v * v, v)          # [(a,b), d]
-    B1 = Dv["Tq"][:, :, q, r]                              # [c, d]  (N x K: transB)
-    A2 = Dv["Tq"][:, :, :, p].reshape(v * v, -1)           # [(a,b), l]
-    B2 = Dv["Ov"][:, :, q, r]                              # [l, c]
-    return (A1 @ B1.T - A2 @ B2).reshape(v, v, v)
+    return x_blocks(Dv, p, 0, q, 0, r, 1, 1)[0]
 
 
 def pt_energy(Dv, fo, fv, nocc=None):
@@ -48,11 +75,14 @@ def pt_energy(Dv, fo, fv, nocc=None):
     slots = []
     for i in range(nocc):
         for j in range(i + 1):
-            # one batch over k = 0..j (the device chunks it when memory is short)
+            # one batch over k = 0..j (the device chunks it when memory is short): six launches
+            nb = j + 1
+            F1, F2 = x_blocks(Dv, i, 0, j, 0, 0, 1, nb), x_blocks(Dv, i, 0, 0, 1, j, 0, nb)
+            F3, F4 = x_blocks(Dv, 0, 1, i, 0, j, 0, nb), x_blocks(Dv, 0, 1, j, 0, i, 0, nb)
+            F5, F6 = x_blocks(Dv, j, 0, 0, 1, i, 0, nb), x_blocks(Dv, j, 0, i, 0, 0, 1, nb)
             e_pair = 0.0
             for k in range(j + 1):
-                X1, X2, X3 = X_block(Dv, i, j, k), X_block(Dv, i, k, j), X_block(Dv, k, i, j)
-                X4, X5, X6 = X_block(Dv, k, j, i), X_block(Dv, j, k, i), X_block(Dv, j, i, k)
+                X1, X2, X3, X4, X5, X6 = F1[k], F2[k], F3[k], F4[k], F5[k], F6[k]
                 W = (X1 + X2.transpose(0, 2, 1) + X3.transpose(1, 2, 0) + X4.transpose(2, 1, 0)
                      + X5.transpose(2, 0, 1) + X6.transpose(1, 0, 2))
                 V = (W + Vv[:, :, j, k][None, :, :] * t[i][:, None, None]
