@@ -443,7 +443,7 @@ struct CC {
     // ---- one sweep, replayed from a CUDA graph once the launch sequence is warm ---------------------
     // A sweep is ~100 kernel launches and ~300 stream-ordered allocations; issued one by one the GPU
     // idles whenever the launching thread is descheduled for longer than the queue it has built up
-    // (measured on shared hosts: single sweeps of 9 ms stretched to 15-240 ms).  After two eager sweeps
+    // (measured on shared hosts: single sweeps of 9 ms stretched to 15-240 ms).  After one eager sweep
     // (every lazily built operand copy, kernel attribute and pool block exists) the sweep is captured
     // once per amplitude-buffer parity (T2 -> T2n and back) and replayed with one cudaGraphLaunch, so
     // the host can run arbitrarily far ahead.  Capture failures fall back to eager launches.
@@ -452,10 +452,19 @@ struct CC {
     const double* t2_even = nullptr;
     int eager_sweeps = 0;
     bool graph_ok = true;
+    // Capturing + instantiating the two graphs costs ~80 ms of host time (measured, nbf = 120), so the
+    // driver turns replay on only for long fixed-length runs of launch-bound sweeps (see allow_graphs).
+    bool use_graphs = false;
+    void allow_graphs(int sweeps) {
+        const double fl = 2.0 * (double)(o * o) * (double)(v * v) * (double)(v * v) +
+                          22.0 * (double)(o * o * o) * (double)(v * v * v);
+        use_graphs = sweeps >= 12 && fl < 1.5e12;     // < ~50 ms per sweep
+    }
 
     void sweep() {
         static const bool off = getenv("JUES_B200_NO_GRAPH") != nullptr || getenv("JUES_B200_TRACE") != nullptr;
-        if (off || !graph_ok || ctx->nranks != 1 || eager_sweeps < 2) {
+        // the first sweep runs eagerly: it builds every lazily created operand copy / kernel attribute
+        if (off || !use_graphs || !graph_ok || ctx->nranks != 1 || eager_sweeps < 1) {
             iterate();
             ++eager_sweeps;
             return;
@@ -583,6 +592,7 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
     cc.build_integrals(gao);
     cc.register_static();
     cc.guess(guess_mode);
+    if (!cb) cc.allow_graphs(maxit);
     CCResult res;
     res.e_hist.resize(maxit + 1);
     std::vector<double> h1, h2;

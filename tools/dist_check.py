@@ -45,6 +45,29 @@ def main():
             assert terr < 1e-12, terr
             print(f"N={N} o={o} world={world} errs={['%.1e' % x for x in errs]} comm={ctx.comm_counters()}", flush=True)
             worst = max(worst, max(errs[0], errs[1], errs[4], errs[5], errs[7]) / 1e-10, max(errs[2], errs[3], errs[6]) / 1e-9)
+    # section-8f entry points on the same communicator: AutoRCCSD (non-canonical Fock, frozen core,
+    # convergence loop) with the (T) correction (pairs dealt to the ranks, scalar all-reduce) and mRCCD
+    for (N, o, seed, fcn) in [(14, 5, 17, 1), (16, 4, 2, 0)]:
+        g, h, Ca, eps = jb.synth.noncanonical_inputs(N, o, seed=seed)
+        w = jb.Wfn(o, N - o, eps, Ca[:, :o].copy(), Ca[:, o:].copy(), g, hao=h, Ca=Ca)
+        r = jb.AutoRCCSD.do_rccsd(w, ctx=ctx, do_pT=True, fcn=fcn, _return_all=True)
+        gc, Cao, Cav, _ = jb.synth.dense_inputs(N, o, seed=seed)
+        wc = jb.Wfn(o, N - o, eps, Cao, Cav, gc)
+        m = jb.mRCCD.do_rccd(wc, ctx=ctx, _return_all=True)
+        t = torch.tensor([r["ecc"], r["ept"], float(r["iterations"]), float(np.abs(r["T2"]).sum()), m["ecc"]],
+                         dtype=torch.float64, device="cuda")
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert float((hi - lo).abs().max()) == 0.0, "ranks disagree (auto)"
+        if rank == 0:
+            from oracle import jues_oracle as orc, jues_oracle_auto as oa
+            wo = orc.Wfn(o, N - o, eps, Ca[:, :o].copy(), Ca[:, o:].copy(), g, hao=h, Ca=Ca)
+            ro = oa.do_auto_rccsd(wo, do_pT=True, fcn=fcn, return_all=True)
+            mo = oa.do_mrccd(orc.Wfn(o, N - o, eps, Cao, Cav, gc), return_all=True)
+            errs = [abs(r["ecc"] - ro["ecc"]), abs(r["ept"] - ro["ept"]), np.abs(r["T2"] - ro["T2"]).max(),
+                    float(abs(r["iterations"] - ro["iterations"])), abs(m["ecc"] - mo["ecc"])]
+            print(f"AUTO N={N} o={o} fcn={fcn} world={world} errs={['%.1e' % x for x in errs]}", flush=True)
+            worst = max(worst, errs[0] / 1e-10, errs[1] / 1e-10, errs[2] / 1e-9, errs[3] * 10, errs[4] / 1e-6)
     ok = torch.tensor([1.0 if worst <= 1.0 else 0.0], device="cuda")
     dist.broadcast(ok, src=0)
     if rank == 0:
