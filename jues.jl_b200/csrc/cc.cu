@@ -16,6 +16,7 @@
 #include "cc.h"
 #include "dist.h"
 #include "pt.h"
+#include "dgemm.h"
 
 #include <algorithm>
 #include <cmath>
@@ -162,6 +163,11 @@ struct CC {
     // last-index slabs of the large classes:  W4[e,f,a,b] = <ef|ab>,  OA[e,f,m,b] = <ef|mb>
     // (= ovvv[m,b,e,f]),  OB[a,j,e,b] = <aj|eb> (= (ae|jb)),  b in the slab
     DTen W4, OA, OB;
+    // single rank: <vv|vv> packed into its (ef)-symmetric and -antisymmetric parts [W+ | W-]
+    // (tensor_ops.h: half the ladder flops); W4 itself is released once they are built
+    DTen Wsa;
+    int64_t sa_ld = 0;
+    bool sa_ladder = false;
     // static combinations
     DTen Vt, oovo, ooov_t;
     // off-diagonal Fock blocks of a non-canonical reference (AutoRCCSD.jl:218-231), zero diagonals,
@@ -260,6 +266,14 @@ struct CC {
         }
         tws.buf[0].release(); tws.buf[1].release();
         Timer t(ctx, "cc.static");
+        if (ctx->nranks == 1 && getenv("JUES_B200_PLAIN_LADDER") == nullptr) {
+            sa_ld = round_up(sa_pairs(v), 2);
+            Wsa.alloc(ctx, sa_ld, sa_ld, 2);
+            Wsa.buf.zero();
+            pack_vvvv_sa(ctx, W4.p(), v, sa_ld, Wsa.p());
+            W4.release();
+            sa_ladder = true;
+        }
         const size_t n2 = (size_t)(o * o * v * v);
         Vt.alloc(ctx, o, o, v, v);
         axpby(ctx, n2, 2.0, V.p(), 0.0, Vt.p());
@@ -404,7 +418,22 @@ struct CC {
         TraceTimer* tr_lad = new TraceTimer(ctx, "cc.part.ladders+H");
         DTen Lpp(ctx, o, o, v, vs), Lhh(ctx, o, o, v, vs), Hfull(ctx, o, o, v, v);
         const Ten H = last_slab(Hfull, b0, vs);
-        contract(ctx, 1.0, tauv, "ijef", W4, "efab", 0.0, Lpp, "ijab");
+        if (sa_ladder) {
+            // tau.vvvv through the packed symmetric / antisymmetric parts: one batched GEMM of two
+            // (o^2 x np)(np x np) products, np = v(v+1)/2
+            const int64_t oo = o * o, np = sa_pairs(v);
+            DBuf Tpm(ctx, (size_t)(2 * oo * sa_ld)), Lpm(ctx, (size_t)(2 * oo * sa_ld));
+            pack_tau_sa(ctx, tauv.p, oo, v, sa_ld, Tpm.p);
+            GemmCall g;
+            g.M = oo; g.N = np; g.K = np; g.batch = 2;
+            g.A = Tpm.p; g.lda = oo; g.strideA = oo * sa_ld;
+            g.B = Wsa.p(); g.ldb = sa_ld; g.strideB = sa_ld * sa_ld;
+            g.C = Lpm.p; g.ldc = oo; g.strideC = oo * sa_ld;
+            dgemm(ctx, g);
+            unpack_ladder_sa(ctx, Lpm.p, oo, v, sa_ld, Lpp.p());
+        } else {
+            contract(ctx, 1.0, tauv, "ijef", W4, "efab", 0.0, Lpp, "ijab");
+        }
         contract(ctx, 1.0, Wpp, "mnij", tau_S, "mnab", 0.0, Lhh, "ijab");
         // ---- half residual H for the slab (its (ij)(ab) image is added by residual_finish) ----------
         contract(ctx, 1.0, T, "ijae", last_slab(FaeTt, b0, vs), "eb", 0.0, H, "ijab");
@@ -543,7 +572,7 @@ struct CC {
         pcache.clear();
         OB.release(); J.release(); oooo.release(); Vt.release(); oovo.release(); ooov_t.release();
         T2n.release();
-        DBuf scratch = std::move(W4.buf);     // the <vv|vv> slab becomes the triples' work space
+        DBuf scratch = std::move(sa_ladder ? Wsa.buf : W4.buf);     // <vv|vv> becomes the triples' work space
         const int64_t K = v + o;
         TraceTimer* tp = new TraceTimer(ctx, "pt.prepare");
         DTen Acat(ctx, v, v, o, K), Bq(ctx, v, o, K, o), Br(ctx, v, o, K, o), Vv(ctx, v, v, o, o);

@@ -322,6 +322,59 @@ __global__ void sqdiff_kernel(const double* __restrict__ x, const double* __rest
     if (threadIdx.x == 0) partial[blockIdx.x] = r;
 }
 
+// P = e(e+1)/2 + f with 0 <= f <= e
+__device__ __forceinline__ void pair_decode(long long P, int* e, int* f) {
+    long long ee = (long long)((sqrt(8.0 * (double)P + 1.0) - 1.0) * 0.5);
+    while (ee * (ee + 1) / 2 > P) --ee;
+    while ((ee + 1) * (ee + 2) / 2 <= P) ++ee;
+    *e = (int)ee;
+    *f = (int)(P - ee * (ee + 1) / 2);
+}
+
+__global__ void pack_vvvv_sa_kernel(const double* __restrict__ W4, int v, long long np, long long ld,
+                                    double* __restrict__ Wp, double* __restrict__ Wm) {
+    const long long total = np * np;
+    for (long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x; L < total;
+         L += (long long)gridDim.x * blockDim.x) {
+        const long long P = L % np, Q = L / np;
+        int e, f, a, b;
+        pair_decode(P, &e, &f);
+        pair_decode(Q, &a, &b);
+        const long long ab = (long long)v * v * (a + (long long)v * b);
+        const double x = W4[e + (long long)v * f + ab], y = W4[f + (long long)v * e + ab];
+        Wp[P + ld * Q] = (e == f) ? 2.0 * x : x + y;
+        Wm[P + ld * Q] = x - y;
+    }
+}
+
+__global__ void pack_tau_sa_kernel(const double* __restrict__ tau, int oo, int v, long long np,
+                                   double* __restrict__ Tp, double* __restrict__ Tm) {
+    for (long long P = blockIdx.x; P < np; P += gridDim.x) {
+        int e, f;
+        pair_decode(P, &e, &f);
+        const double* __restrict__ x = tau + (long long)oo * (e + (long long)v * f);
+        const double* __restrict__ y = tau + (long long)oo * (f + (long long)v * e);
+        for (int ij = threadIdx.x; ij < oo; ij += blockDim.x) {
+            const double xv = x[ij], yv = y[ij];
+            Tp[ij + (long long)oo * P] = (e == f) ? xv : xv + yv;
+            Tm[ij + (long long)oo * P] = xv - yv;
+        }
+    }
+}
+
+__global__ void unpack_ladder_sa_kernel(const double* __restrict__ Lp, const double* __restrict__ Lm, int oo,
+                                        int v, double* __restrict__ out) {
+    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
+        const int a = (int)(ab % v), b = (int)(ab / v);
+        const long long hi = a > b ? a : b, lo = a > b ? b : a;
+        const long long Q = hi * (hi + 1) / 2 + lo;
+        const double s = a > b ? 0.5 : (a < b ? -0.5 : 0.0);
+        const double* __restrict__ lp = Lp + (long long)oo * Q;
+        const double* __restrict__ lm = Lm + (long long)oo * Q;
+        for (int ij = threadIdx.x; ij < oo; ij += blockDim.x) out[ij + (long long)oo * ab] = 0.5 * lp[ij] + s * lm[ij];
+    }
+}
+
 __global__ void to_float32_kernel(const double* __restrict__ x, const double* __restrict__ y, long long n,
                                   float* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -609,6 +662,28 @@ void sqdiff_async(jues_ctx* ctx, size_t n, const double* x, const double* y, dou
     sqdiff_kernel<<<blocks, 256, 0, ctx->stream>>>(x, y, (long long)n, ctx->red_dev);
     AUX_LAUNCHED(ctx);
     final_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, blocks, dev_out);
+    AUX_LAUNCHED(ctx);
+}
+
+void pack_vvvv_sa(jues_ctx* ctx, const double* W4, int64_t v, int64_t ld, double* Wpm) {
+    const int64_t np = sa_pairs(v);
+    pack_vvvv_sa_kernel<<<ew_grid(ctx, (size_t)(np * np), 256), 256, 0, ctx->stream>>>(W4, (int)v, np, ld, Wpm,
+                                                                                     Wpm + ld * ld);
+    AUX_LAUNCHED(ctx);
+}
+
+void pack_tau_sa(jues_ctx* ctx, const double* tau, int64_t oo, int64_t v, int64_t ld, double* Tpm) {
+    const int64_t np = sa_pairs(v);
+    const int threads = oo >= 256 ? 256 : (oo >= 128 ? 128 : 64);
+    long long blocks = std::min<long long>(np, (long long)ctx->sm_count * 16);
+    pack_tau_sa_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(tau, (int)oo, (int)v, np, Tpm, Tpm + oo * ld);
+    AUX_LAUNCHED(ctx);
+}
+
+void unpack_ladder_sa(jues_ctx* ctx, const double* Lpm, int64_t oo, int64_t v, int64_t ld, double* out) {
+    const int threads = oo >= 256 ? 256 : (oo >= 128 ? 128 : 64);
+    long long blocks = std::min<long long>(v * v, (long long)ctx->sm_count * 16);
+    unpack_ladder_sa_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(Lpm, Lpm + oo * ld, (int)oo, (int)v, out);
     AUX_LAUNCHED(ctx);
 }
 

@@ -89,6 +89,21 @@ void dot_axpby(jues_ctx* ctx, size_t n, double alpha, const double* x, const dou
 // dev_out[0] = sum_k (x[k] - y[k])^2   (deterministic two-pass tree, no host synchronisation)
 void sqdiff_async(jues_ctx* ctx, size_t n, const double* x, const double* y, double* dev_out);
 
+// ---- symmetric / antisymmetric particle-particle ladder ---------------------------------------------
+// sum_ef tau[ij,ef] <ef|ab> = 1/2 sum_{e>=f} tau+[ij,(ef)] W+[(ef),(ab)] + 1/2 sum_{e>f} tau-[ij,(ef)] W-[(ef),(ab)]
+// with x+- = x[ef] +- x[fe] (the e == f member of the + part counted once in tau+, twice in W+), because
+// <ef|ab> = <fe|ba>: W+ is symmetric and W- antisymmetric in (a,b), so only a >= b is computed -- half the
+// flops of the plain (o^2 x v^2)(v^2 x v^2) product.  Pairs are packed as P(e,f) = e(e+1)/2 + f, e >= f;
+// both parts use the same np = v(v+1)/2 pair space (the diagonal of the - part is zero), leading
+// dimension ld = np rounded up to even.
+inline int64_t sa_pairs(int64_t v) { return v * (v + 1) / 2; }
+// Wpm[0] = W+ (ld x ld), Wpm[1] = W- from W4[e,f,a,b] = <ef|ab> (v,v,v,v).  Once per calculation.
+void pack_vvvv_sa(jues_ctx* ctx, const double* W4, int64_t v, int64_t ld, double* Wpm);
+// Tpm[0] = tau+ (oo x ld), Tpm[1] = tau- from tau[i,j,e,f] (oo = o*o rows).  Once per sweep.
+void pack_tau_sa(jues_ctx* ctx, const double* tau, int64_t oo, int64_t v, int64_t ld, double* Tpm);
+// out[ij,a,b] = 1/2 (L+[ij,(ab)] + sign(a-b) L-[ij,(ab)]),  Lpm = [L+ | L-] (oo x ld each)
+void unpack_ladder_sa(jues_ctx* ctx, const double* Lpm, int64_t oo, int64_t v, int64_t ld, double* out);
+
 // ---- mRCCD's DIIS keeps its vectors in Float32 (mRCCD.jl:64-65,171,175) --------------------------
 // out32[k] = float(x[k] - y[k])   (y nullable: plain conversion)
 void to_float32(jues_ctx* ctx, size_t n, const double* x, const double* y, float* out32);

@@ -123,3 +123,35 @@ def rccsd_iteration(I, t, T, Dia, D, fock=None):
     H -= es("ma,mjib->ijab", t, ooov)
     R2 = V + Lpp + Lhh + H + P(H)
     return R1 / Dia, R2 / D
+
+
+# ------------------------------------------------------------------------------------------
+# symmetric / antisymmetric particle-particle ladder (tensor_ops.cu: pack_vvvv_sa, pack_tau_sa,
+# unpack_ladder_sa; cc.cu: sa_ladder)
+# ------------------------------------------------------------------------------------------
+def sa_ladder(tau, W4):
+    """sum_ef tau[i,j,e,f] W4[e,f,a,b] (W4[e,f,a,b] = <ef|ab> = W4[f,e,b,a]) through the packed pair
+    space P(e,f) = e(e+1)/2 + f, e >= f, exactly as the device does it: two (o^2 x np)(np x np)
+    products, np = v(v+1)/2, instead of one (o^2 x v^2)(v^2 x v^2)."""
+    o, v = tau.shape[0], tau.shape[2]
+    pairs = [(e, f) for e in range(v) for f in range(e + 1)]
+    n = len(pairs)
+    Tp, Tm = np.zeros((o * o, n)), np.zeros((o * o, n))
+    Wp, Wm = np.zeros((n, n)), np.zeros((n, n))
+    for P, (e, f) in enumerate(pairs):
+        x, y = tau[:, :, e, f].ravel(order="F"), tau[:, :, f, e].ravel(order="F")
+        Tp[:, P] = x if e == f else x + y
+        Tm[:, P] = x - y
+        for Q, (a, b) in enumerate(pairs):
+            xx, yy = W4[e, f, a, b], W4[f, e, a, b]
+            Wp[P, Q] = 2 * xx if e == f else xx + yy
+            Wm[P, Q] = xx - yy
+    Lp, Lm = Tp @ Wp, Tm @ Wm
+    out = np.zeros((o, o, v, v))
+    for a in range(v):
+        for b in range(v):
+            hi, lo = max(a, b), min(a, b)
+            Q = hi * (hi + 1) // 2 + lo
+            s = 0.5 if a > b else (-0.5 if a < b else 0.0)
+            out[:, :, a, b] = (0.5 * Lp[:, Q] + s * Lm[:, Q]).reshape(o, o, order="F")
+    return out

@@ -126,3 +126,19 @@ def test_flop_model_matches_the_survey_table():
     assert abs(f.rccsd_iter_alg(20, 100) / 2.74e11 - 1) < 3e-3
     assert f.ladder_flops(60, 400) == 2 * 60**2 * 400**4
     assert f.tei_flops_best(50, 5, 45, 5, 45, streamed=True) >= f.tei_flops_best(50, 5, 45, 5, 45)
+
+
+def test_symmetric_antisymmetric_ladder_identity():
+    """The packed-pair pp-ladder the device executes on one rank == the plain tau.vvvv contraction."""
+    import numpy as np
+    import factorized_model as fm
+    from jues.jl_b200 import synth
+    from oracle import jues_oracle as orc
+    g, Cao, Cav, eps = synth.dense_inputs(9, 3, seed=4)
+    I = fm.unique_integrals(g, Cao, Cav)
+    w = orc.Wfn(3, 6, eps, Cao, Cav, g)
+    e, T1, T2 = orc.do_rccsd(w, maxit=2, return_T=True)
+    tau = T2 + np.einsum("ia,jb->ijab", T1, T1)
+    W4 = np.ascontiguousarray(I["vvvv"].transpose(2, 3, 0, 1))       # W4[e,f,a,b] = <ef|ab> = vvvv[a,b,e,f]
+    ref = np.einsum("ijef,efab->ijab", tau, W4)
+    assert np.abs(fm.sa_ladder(tau, W4) - ref).max() < 1e-14 * max(1.0, np.abs(ref).max())
