@@ -13,8 +13,9 @@ CPU".  One JSON line is printed by rank 0:
     tei_transform(gao, C) of the same AO tensor, executed flops = 8 N^5).
   * `e2e` is the same metric through the reference-facing C-ABI call with HOST buffers (pinned):
     one complete do_rccsd (H2D of gao/C/eps + integral transformation + 40 sweeps + energy D2H).
-  * `roofline` is the dominant kernel (the TMA+DMMA FP64 GEMM at the particle-particle-ladder
-    shape), timed live with CUDA events on the library's stream, against the measured cuBLAS FP64
+  * `roofline` is the dominant kernel (the TMA+DMMA FP64 GEMM at the shape with the largest share of
+    the sweep: the ring products (ov x ov)(ov x ov) on one GPU, the particle-particle-ladder slab on
+    several), timed live with CUDA events on the library's stream, against the measured cuBLAS FP64
     peak of this pool (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json records no FP64 figure).
   * `cpu_baseline` is the oracle (numpy restatement of the reference's literal algorithm, "port")
     timed on this box's host cores on a bounded sample.
@@ -181,8 +182,8 @@ def fp64_peak():
         return 37.0, "fallback: DMMA issue-rate ceiling 148 SM x 64 FMA/clk x 1.965 GHz"
 
 
-def traffic_from_profile():
-    p = os.path.join(ROOT, "profiles", "ncu_dgemm_ladder_r01.json")
+def traffic_from_profile(name="ncu_dgemm_ladder_r01.json"):
+    p = os.path.join(ROOT, "profiles", name)
     try:
         return float(json.load(open(p))["dram_bytes_per_launch"])
     except Exception:
@@ -355,14 +356,22 @@ def gpu_arm(args, rank, world):
     clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel, timed live (CUDA events on the library's stream) ----
-    M, Nn, K = o * o, v * (v // world), v * v            # pp-ladder tau(ij,ef) x <ef|ab>, this rank's slab
-    ms_gemm = ctx.gemm_bench("N", "N", M, Nn, K, reps=5)
+    if world == 1:
+        # one rank: the pp-ladder runs in the packed symmetric/antisymmetric pair space (half its flops),
+        # which leaves the seven ring products (ov x ov)(ov x ov) as the largest share of the sweep
+        # (41 % of its kernel time, profiles/ncu_launches_rccsd_sweep_r01b.csv)
+        M = Nn = K = o * v
+        tA, shape, prof = "T", f"ring GEMM (ov x ov)(ov x ov) M=N=K={M}", "ncu_dgemm_ring_r01.json"
+    else:
+        M, Nn, K = o * o, v * (v // world), v * v        # pp-ladder tau(ij,ef) x <ef|ab>, this rank's slab
+        tA, shape, prof = "N", f"pp-ladder GEMM M={M} N={Nn} K={K}", "ncu_dgemm_ladder_r01.json"
+    ms_gemm = ctx.gemm_bench(tA, "N", M, Nn, K, reps=5)
     peak, peak_src = fp64_peak()
     ach = 2.0 * M * Nn * K / ms_gemm * 1e-9
     roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": traffic_from_profile(),
+                "traffic": traffic_from_profile(prof) if (world == 1 and NBF == 120) or prof.endswith("ladder_r01.json") else None,
                 "kernel": "jues::gemm::dgemm_tma_dmma (FP64 DMMA.8x8x4 fed by TMA)",
-                "shape": f"pp-ladder GEMM M={M} N={Nn} K={K}", "ms_per_launch": ms_gemm, "peak_source": peak_src,
+                "shape": shape, "ms_per_launch": ms_gemm, "peak_source": peak_src,
                 "sweep_frac_of_peak": flops_step / (ms_step * 1e-3) * 1e-12 / peak}
 
     # ---- max over ranks -----------------------------------------------------------------------

@@ -1,22 +1,13 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_auto.py tests/test_golden.py -q -m gpu -k "rccsd or rccd or auto or pT or triples or golden or mrccd" --tb=short -p no:cacheprovider 2>&1 | tail -n 15 | cut -c1-200
-for n in 1 2 3; do
-for cfg in "JUES_B200_NO_GRAPH=1 --steps 60" "X=1 --steps 60"; do
-  envs=${cfg%% *}; fl=${cfg#* }
-  env $envs BENCH_SAMPLER_PERIOD=0.1 timeout 200 python bench.py --no-cpu-baseline $fl > gpurun_out/b.json 2> gpurun_out/b.err
-  python - "$cfg" <<'PY'
-import json,sys
-d=json.load(open('gpurun_out/b.json')); s=d['ms_each_step_rank0']; h=d['host_issue_ms_rank0']
-print(sys.argv[1], 'ms_per_step', round(d['ms_per_step'],3), 'max', max(s), 'n>10ms', sum(1 for x in s if x>10), 'graph', d['graph_replayed_sweeps'], 'host_issue_last_ms', h[-1], 'gpu_total_ms', round(sum(s),1), 'e2e', round(d['e2e']['s_per_do_rccsd'],4))
-PY
-done; done
-cp gpurun_out/b.json gpurun_out/bench_graph.json
-JUES_B200_TRACE=1 timeout 240 python tools/auto_bench.py --nbf 120 --nocc 20 --out gpurun_out/auto_bench_c3_trace.json > gpurun_out/auto_bench.log 2>&1
-timeout 240 python tools/auto_bench.py --nbf 120 --nocc 20 --out gpurun_out/auto_bench_c3.json > gpurun_out/auto_bench.log 2>&1
-python - <<'PY'
-import json
-for f in ('auto_bench_c3_trace','auto_bench_c3'):
-    d=json.load(open(f'gpurun_out/{f}.json'))
-    a=d['auto_rccsd_canonical']; print(f,{k:a[k] for k in ('iterations','ept','cc.triples_ms','pt_tflops','pt_frac_of_fp64_peak','ms_per_sweep_median','wall_s')}, {k:v for k,v in a.get('trace_ms_sum',{}).items() if k.startswith('pt.')}, d['auto_rccsd_noncanonical']['ms_per_sweep_median'], d['auto_rccsd_noncanonical']['wall_s'], d['mrccd_diis']['wall_s'])
-PY
+timeout 120 ncu --set full --clock-control none --import-source on -k regex:dgemm_tma_dmma -s 2 -c 1 -f -o gpurun_out/ncu_gemm_ring python tools/gemm_one.py T N 2000 2000 2000 > gpurun_out/ncu_gemm_ring.log 2>&1
+echo "ring exit $?"; tail -n 2 gpurun_out/ncu_gemm_ring.log
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/ncu_launches_sweep.csv python tools/sweep_for_ncu.py 120 20 3 > gpurun_out/ncu_sweep.log 2>&1
+echo "list exit $?"; wc -l gpurun_out/ncu_launches_sweep.csv
+timeout 200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:dgemm_tma_dmma<0, 1, (80|96|112|128), 128' -s 1 -c 1 -f -o gpurun_out/ncu_gemm_saladder python tools/sweep_for_ncu.py 120 20 2 > gpurun_out/ncu_gemm_saladder.log 2>&1
+echo "saladder exit $?"; tail -n 3 gpurun_out/ncu_gemm_saladder.log | cut -c1-200
+for k in pack_tau_sa_kernel unpack_ladder_sa_kernel; do
+timeout 120 ncu --set full --clock-control none -k regex:$k -s 1 -c 1 -f -o gpurun_out/ncu_$k python tools/sweep_for_ncu.py 120 20 2 > gpurun_out/ncu_$k.log 2>&1
+echo "$k exit $?"
+done
+ls -la gpurun_out/*.ncu-rep
