@@ -369,7 +369,8 @@ def gpu_arm(args, rank, world):
     peak, peak_src = fp64_peak()
     ach = 2.0 * M * Nn * K / ms_gemm * 1e-9
     roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": traffic_from_profile(prof) if (world == 1 and NBF == 120) or prof.endswith("ladder_r01.json") else None,
+                # measured DRAM bytes per launch (ncu --set full) exist for the 1-GPU shape only
+                "traffic": traffic_from_profile(prof) if (world == 1 and NBF == 120) else None,
                 "kernel": "jues::gemm::dgemm_tma_dmma (FP64 DMMA.8x8x4 fed by TMA)",
                 "shape": shape, "ms_per_launch": ms_gemm, "peak_source": peak_src,
                 "sweep_frac_of_peak": flops_step / (ms_step * 1e-3) * 1e-12 / peak}
