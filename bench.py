@@ -363,8 +363,10 @@ def gpu_arm(args, rank, world):
         M = Nn = K = o * v
         tA, shape, prof = "T", f"ring GEMM (ov x ov)(ov x ov) M=N=K={M}", "ncu_dgemm_ring_r01.json"
     else:
-        M, Nn, K = o * o, v * (v // world), v * v        # pp-ladder tau(ij,ef) x <ef|ab>, this rank's slab
-        tA, shape, prof = "N", f"pp-ladder GEMM M={M} N={Nn} K={K}", "ncu_dgemm_ladder_r01.json"
+        # several ranks: this rank's column block of the packed (symmetric/antisymmetric) pp-ladder,
+        # tau+-(ij,(ef)) x W+-((ef),(ab)): two such products per sweep in one batched launch
+        M, Nn, K = o * o, (v // world) * (v // 2 + 1), v * (v + 1) // 2
+        tA, shape, prof = "N", f"packed pp-ladder GEMM M={M} N={Nn} K={K} (x2 per sweep)", "ncu_dgemm_ladder_r01.json"
     ms_gemm = ctx.gemm_bench(tA, "N", M, Nn, K, reps=5)
     peak, peak_src = fp64_peak()
     ach = 2.0 * M * Nn * K / ms_gemm * 1e-9

@@ -163,10 +163,11 @@ struct CC {
     // last-index slabs of the large classes:  W4[e,f,a,b] = <ef|ab>,  OA[e,f,m,b] = <ef|mb>
     // (= ovvv[m,b,e,f]),  OB[a,j,e,b] = <aj|eb> (= (ae|jb)),  b in the slab
     DTen W4, OA, OB;
-    // single rank: <vv|vv> packed into its (ef)-symmetric and -antisymmetric parts [W+ | W-]
-    // (tensor_ops.h: half the ladder flops); W4 itself is released once they are built
+    // <vv|vv> packed into its (ef)-symmetric and -antisymmetric parts [W+ | W-] for this rank's column
+    // block of the output-pair space (tensor_ops.h: half the ladder flops); W4 itself is released once
+    // they are built
     DTen Wsa;
-    int64_t sa_ld = 0;
+    int64_t sa_ld = 0, sa_nq = 0;
     bool sa_ladder = false;
     // static combinations
     DTen Vt, oovo, ooov_t;
@@ -266,11 +267,12 @@ struct CC {
         }
         tws.buf[0].release(); tws.buf[1].release();
         Timer t(ctx, "cc.static");
-        if (ctx->nranks == 1 && getenv("JUES_B200_PLAIN_LADDER") == nullptr) {
+        if (getenv("JUES_B200_PLAIN_LADDER") == nullptr) {
             sa_ld = round_up(sa_pairs(v), 2);
-            Wsa.alloc(ctx, sa_ld, sa_ld, 2);
+            sa_nq = vs * sa_slots(v);
+            Wsa.alloc(ctx, sa_ld, sa_nq, 2);
             Wsa.buf.zero();
-            pack_vvvv_sa(ctx, W4.p(), v, sa_ld, Wsa.p());
+            pack_vvvv_sa(ctx, W4.p(), v, b0, vs, sa_ld, Wsa.p());
             W4.release();
             sa_ladder = true;
         }
@@ -420,17 +422,23 @@ struct CC {
         const Ten H = last_slab(Hfull, b0, vs);
         if (sa_ladder) {
             // tau.vvvv through the packed symmetric / antisymmetric parts: one batched GEMM of two
-            // (o^2 x np)(np x np) products, np = v(v+1)/2
-            const int64_t oo = o * o, np = sa_pairs(v);
-            DBuf Tpm(ctx, (size_t)(2 * oo * sa_ld)), Lpm(ctx, (size_t)(2 * oo * sa_ld));
+            // (o^2 x np)(np x nq) products, np = v(v+1)/2 summed pairs, nq = this rank's block of the
+            // ~v^2/2 output pairs; the blocks of the other ranks are all-gathered (o^2 v^2 doubles in all)
+            const int64_t oo = o * o, np = sa_pairs(v), nq_all = v * sa_slots(v);
+            DBuf Tpm(ctx, (size_t)(2 * oo * sa_ld)), Lpm(ctx, (size_t)(2 * oo * nq_all));
             pack_tau_sa(ctx, tauv.p, oo, v, sa_ld, Tpm.p);
             GemmCall g;
-            g.M = oo; g.N = np; g.K = np; g.batch = 2;
+            g.M = oo; g.N = sa_nq; g.K = np; g.batch = 2;
             g.A = Tpm.p; g.lda = oo; g.strideA = oo * sa_ld;
-            g.B = Wsa.p(); g.ldb = sa_ld; g.strideB = sa_ld * sa_ld;
-            g.C = Lpm.p; g.ldc = oo; g.strideC = oo * sa_ld;
+            g.B = Wsa.p(); g.ldb = sa_ld; g.strideB = sa_ld * sa_nq;
+            g.C = Lpm.p + oo * sa_nq * ctx->rank; g.ldc = oo; g.strideC = oo * nq_all;
             dgemm(ctx, g);
-            unpack_ladder_sa(ctx, Lpm.p, oo, v, sa_ld, Lpp.p());
+            {
+                TraceTimer tt(ctx, "cc.comm.gatherL");
+                all_gather_inplace(ctx, Lpm.p, (size_t)(oo * sa_nq));
+                all_gather_inplace(ctx, Lpm.p + oo * nq_all, (size_t)(oo * sa_nq));
+            }
+            unpack_ladder_sa(ctx, Lpm.p, oo, v, b0, vs, Lpp.p());
         } else {
             contract(ctx, 1.0, tauv, "ijef", W4, "efab", 0.0, Lpp, "ijab");
         }

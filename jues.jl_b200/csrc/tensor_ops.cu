@@ -331,19 +331,30 @@ __device__ __forceinline__ void pair_decode(long long P, int* e, int* f) {
     *f = (int)(P - ee * (ee + 1) / 2);
 }
 
-__global__ void pack_vvvv_sa_kernel(const double* __restrict__ W4, int v, long long np, long long ld,
-                                    double* __restrict__ Wp, double* __restrict__ Wm) {
-    const long long total = np * np;
+// column (zl, t) of the output-pair space: partner w of z = b0 + zl at slot t (or -1 for the pad slot)
+__device__ __forceinline__ int sa_partner(int z, int t, int v) {
+    const int n_low = z / 2 + 1;                       // partners w <= z: z%2, z%2+2, .., z
+    const int w = t < n_low ? (z & 1) + 2 * t : z + 1 + 2 * (t - n_low);
+    return w < v ? w : -1;
+}
+
+__global__ void pack_vvvv_sa_kernel(const double* __restrict__ W4, int v, int b0, int vs, long long np,
+                                    long long ldk, double* __restrict__ Wp, double* __restrict__ Wm) {
+    const int hv = v / 2 + 1;
+    const long long total = np * vs * hv;
     for (long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x; L < total;
          L += (long long)gridDim.x * blockDim.x) {
-        const long long P = L % np, Q = L / np;
-        int e, f, a, b;
+        const long long P = L % np, col = L / np;
+        const int zl = (int)(col / hv), t = (int)(col % hv);
+        const int z = b0 + zl;
+        const int w = sa_partner(z, t, v);
+        if (w < 0) continue;                           // pad slot stays zero
+        int e, f;
         pair_decode(P, &e, &f);
-        pair_decode(Q, &a, &b);
-        const long long ab = (long long)v * v * (a + (long long)v * b);
-        const double x = W4[e + (long long)v * f + ab], y = W4[f + (long long)v * e + ab];
-        Wp[P + ld * Q] = (e == f) ? 2.0 * x : x + y;
-        Wm[P + ld * Q] = x - y;
+        const long long wz = (long long)v * v * (w + (long long)v * zl);
+        const double x = W4[e + (long long)v * f + wz], y = W4[f + (long long)v * e + wz];   // <ef|wz>, <fe|wz>
+        Wp[P + ldk * col] = (e == f) ? 2.0 * x : x + y;
+        Wm[P + ldk * col] = (w > z) ? x - y : y - x;   // <ef|hi lo> - <fe|hi lo>, (hi,lo) = the ordered pair
     }
 }
 
@@ -363,11 +374,15 @@ __global__ void pack_tau_sa_kernel(const double* __restrict__ tau, int oo, int v
 }
 
 __global__ void unpack_ladder_sa_kernel(const double* __restrict__ Lp, const double* __restrict__ Lm, int oo,
-                                        int v, double* __restrict__ out) {
-    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
-        const int a = (int)(ab % v), b = (int)(ab / v);
-        const long long hi = a > b ? a : b, lo = a > b ? b : a;
-        const long long Q = hi * (hi + 1) / 2 + lo;
+                                        int v, int b0, int vs, double* __restrict__ out) {
+    const int hv = v / 2 + 1;
+    for (long long ab = blockIdx.x; ab < (long long)v * vs; ab += gridDim.x) {
+        const int a = (int)(ab % v), b = b0 + (int)(ab / v);
+        const int hi = a > b ? a : b, lo = a > b ? b : a;
+        const int z = ((hi - lo) & 1) ? lo : hi, w = ((hi - lo) & 1) ? hi : lo;
+        const int n_low = z / 2 + 1;
+        const int t = w <= z ? (w - (z & 1)) / 2 : n_low + (w - z - 1) / 2;
+        const long long Q = (long long)z * hv + t;
         const double s = a > b ? 0.5 : (a < b ? -0.5 : 0.0);
         const double* __restrict__ lp = Lp + (long long)oo * Q;
         const double* __restrict__ lm = Lm + (long long)oo * Q;
@@ -665,25 +680,27 @@ void sqdiff_async(jues_ctx* ctx, size_t n, const double* x, const double* y, dou
     AUX_LAUNCHED(ctx);
 }
 
-void pack_vvvv_sa(jues_ctx* ctx, const double* W4, int64_t v, int64_t ld, double* Wpm) {
-    const int64_t np = sa_pairs(v);
-    pack_vvvv_sa_kernel<<<ew_grid(ctx, (size_t)(np * np), 256), 256, 0, ctx->stream>>>(W4, (int)v, np, ld, Wpm,
-                                                                                     Wpm + ld * ld);
+void pack_vvvv_sa(jues_ctx* ctx, const double* W4, int64_t v, int64_t b0, int64_t vs, int64_t ldk, double* Wpm) {
+    const int64_t np = sa_pairs(v), nq = vs * sa_slots(v);
+    pack_vvvv_sa_kernel<<<ew_grid(ctx, (size_t)(np * nq), 256), 256, 0, ctx->stream>>>(
+        W4, (int)v, (int)b0, (int)vs, np, ldk, Wpm, Wpm + ldk * nq);
     AUX_LAUNCHED(ctx);
 }
 
-void pack_tau_sa(jues_ctx* ctx, const double* tau, int64_t oo, int64_t v, int64_t ld, double* Tpm) {
+void pack_tau_sa(jues_ctx* ctx, const double* tau, int64_t oo, int64_t v, int64_t ldk, double* Tpm) {
     const int64_t np = sa_pairs(v);
     const int threads = oo >= 256 ? 256 : (oo >= 128 ? 128 : 64);
     long long blocks = std::min<long long>(np, (long long)ctx->sm_count * 16);
-    pack_tau_sa_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(tau, (int)oo, (int)v, np, Tpm, Tpm + oo * ld);
+    pack_tau_sa_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(tau, (int)oo, (int)v, np, Tpm, Tpm + oo * ldk);
     AUX_LAUNCHED(ctx);
 }
 
-void unpack_ladder_sa(jues_ctx* ctx, const double* Lpm, int64_t oo, int64_t v, int64_t ld, double* out) {
+void unpack_ladder_sa(jues_ctx* ctx, const double* Lpm, int64_t oo, int64_t v, int64_t b0, int64_t vs, double* out) {
     const int threads = oo >= 256 ? 256 : (oo >= 128 ? 128 : 64);
-    long long blocks = std::min<long long>(v * v, (long long)ctx->sm_count * 16);
-    unpack_ladder_sa_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(Lpm, Lpm + oo * ld, (int)oo, (int)v, out);
+    long long blocks = std::min<long long>(v * vs, (long long)ctx->sm_count * 16);
+    if (blocks < 1) return;
+    unpack_ladder_sa_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
+        Lpm, Lpm + oo * v * sa_slots(v), (int)oo, (int)v, (int)b0, (int)vs, out);
     AUX_LAUNCHED(ctx);
 }
 

@@ -92,17 +92,26 @@ void sqdiff_async(jues_ctx* ctx, size_t n, const double* x, const double* y, dou
 // ---- symmetric / antisymmetric particle-particle ladder ---------------------------------------------
 // sum_ef tau[ij,ef] <ef|ab> = 1/2 sum_{e>=f} tau+[ij,(ef)] W+[(ef),(ab)] + 1/2 sum_{e>f} tau-[ij,(ef)] W-[(ef),(ab)]
 // with x+- = x[ef] +- x[fe] (the e == f member of the + part counted once in tau+, twice in W+), because
-// <ef|ab> = <fe|ba>: W+ is symmetric and W- antisymmetric in (a,b), so only a >= b is computed -- half the
-// flops of the plain (o^2 x v^2)(v^2 x v^2) product.  Pairs are packed as P(e,f) = e(e+1)/2 + f, e >= f;
-// both parts use the same np = v(v+1)/2 pair space (the diagonal of the - part is zero), leading
-// dimension ld = np rounded up to even.
+// <ef|ab> = <fe|ba>: W+ is symmetric and W- antisymmetric in (a,b), so each unordered pair {a,b} is
+// computed once -- half the flops of the plain (o^2 x v^2)(v^2 x v^2) product.
+//   * summed pairs (K space): P(e,f) = e(e+1)/2 + f, e >= f, np = v(v+1)/2 (the diagonal of the - part is
+//     zero), leading dimension ldk = np rounded up to even;
+//   * output pairs (N space), laid out so that they shard with the virtual slabs of the CC driver: the
+//     pair {x,y} belongs to the column block of z = max(x,y) when x - y is even, of z = min(x,y) when it
+//     is odd, at position t among z's partners (w = z%2, z%2+2, .., z, then z+1, z+3, ..), i.e. column
+//     Q = z*hv + t with hv = v/2 + 1 slots per z (one is a zero pad when z is odd).  Every z owns ~v/2
+//     pairs, so equal slabs of z are equal shares of the work, and W+-[.,(z,w)] needs only <..|w z>
+//     with z in the rank's slab of the LAST index -- exactly the <vv|vv> slab the rank already holds.
 inline int64_t sa_pairs(int64_t v) { return v * (v + 1) / 2; }
-// Wpm[0] = W+ (ld x ld), Wpm[1] = W- from W4[e,f,a,b] = <ef|ab> (v,v,v,v).  Once per calculation.
-void pack_vvvv_sa(jues_ctx* ctx, const double* W4, int64_t v, int64_t ld, double* Wpm);
-// Tpm[0] = tau+ (oo x ld), Tpm[1] = tau- from tau[i,j,e,f] (oo = o*o rows).  Once per sweep.
-void pack_tau_sa(jues_ctx* ctx, const double* tau, int64_t oo, int64_t v, int64_t ld, double* Tpm);
-// out[ij,a,b] = 1/2 (L+[ij,(ab)] + sign(a-b) L-[ij,(ab)]),  Lpm = [L+ | L-] (oo x ld each)
-void unpack_ladder_sa(jues_ctx* ctx, const double* Lpm, int64_t oo, int64_t v, int64_t ld, double* out);
+inline int64_t sa_slots(int64_t v) { return v / 2 + 1; }
+// Wpm[0] = W+ (ldk x vs*hv), Wpm[1] = W- from the slab W4[e,f,w,z-b0] = <ef|wz>, z in [b0, b0+vs).
+// Wpm must be zero-initialised (pad columns).  Once per calculation.
+void pack_vvvv_sa(jues_ctx* ctx, const double* W4, int64_t v, int64_t b0, int64_t vs, int64_t ldk, double* Wpm);
+// Tpm[0] = tau+ (oo x ldk), Tpm[1] = tau- from tau[i,j,e,f] (oo = o*o rows).  Once per sweep.
+void pack_tau_sa(jues_ctx* ctx, const double* tau, int64_t oo, int64_t v, int64_t ldk, double* Tpm);
+// out[ij,a,b-b0] = 1/2 (L+[ij,Q(a,b)] + sign(a-b) L-[ij,Q(a,b)]) for b in [b0, b0+vs), all a;
+// Lpm = [L+ | L-], each oo x v*hv (ALL column blocks: all-gathered when there are several ranks).
+void unpack_ladder_sa(jues_ctx* ctx, const double* Lpm, int64_t oo, int64_t v, int64_t b0, int64_t vs, double* out);
 
 // ---- mRCCD's DIIS keeps its vectors in Float32 (mRCCD.jl:64-65,171,175) --------------------------
 // out32[k] = float(x[k] - y[k])   (y nullable: plain conversion)

@@ -127,31 +127,78 @@ def rccsd_iteration(I, t, T, Dia, D, fock=None):
 
 # ------------------------------------------------------------------------------------------
 # symmetric / antisymmetric particle-particle ladder (tensor_ops.cu: pack_vvvv_sa, pack_tau_sa,
-# unpack_ladder_sa; cc.cu: sa_ladder)
+# unpack_ladder_sa; cc.cu: sa_ladder) -- same index functions as the kernels
 # ------------------------------------------------------------------------------------------
-def sa_ladder(tau, W4):
-    """sum_ef tau[i,j,e,f] W4[e,f,a,b] (W4[e,f,a,b] = <ef|ab> = W4[f,e,b,a]) through the packed pair
-    space P(e,f) = e(e+1)/2 + f, e >= f, exactly as the device does it: two (o^2 x np)(np x np)
-    products, np = v(v+1)/2, instead of one (o^2 x v^2)(v^2 x v^2)."""
+def sa_partner(z, t, v):
+    """Partner w of z at slot t of z's column block (or -1 for the pad slot)."""
+    n_low = z // 2 + 1
+    w = (z & 1) + 2 * t if t < n_low else z + 1 + 2 * (t - n_low)
+    return w if w < v else -1
+
+
+def sa_column(a, b, v):
+    """Column Q of the unordered pair {a,b} in the output-pair space, hv = v/2+1 slots per z."""
+    hv = v // 2 + 1
+    hi, lo = max(a, b), min(a, b)
+    z, w = (lo, hi) if (hi - lo) & 1 else (hi, lo)
+    n_low = z // 2 + 1
+    t = (w - (z & 1)) // 2 if w <= z else n_low + (w - z - 1) // 2
+    return z * hv + t
+
+
+def sa_pack_tau(tau):
     o, v = tau.shape[0], tau.shape[2]
-    pairs = [(e, f) for e in range(v) for f in range(e + 1)]
-    n = len(pairs)
-    Tp, Tm = np.zeros((o * o, n)), np.zeros((o * o, n))
-    Wp, Wm = np.zeros((n, n)), np.zeros((n, n))
+    pairs = [(e, f) for e in range(v) for f in range(e + 1)]          # P = e(e+1)/2 + f
+    Tp, Tm = np.zeros((o * o, len(pairs))), np.zeros((o * o, len(pairs)))
     for P, (e, f) in enumerate(pairs):
         x, y = tau[:, :, e, f].ravel(order="F"), tau[:, :, f, e].ravel(order="F")
         Tp[:, P] = x if e == f else x + y
         Tm[:, P] = x - y
-        for Q, (a, b) in enumerate(pairs):
-            xx, yy = W4[e, f, a, b], W4[f, e, a, b]
-            Wp[P, Q] = 2 * xx if e == f else xx + yy
-            Wm[P, Q] = xx - yy
-    Lp, Lm = Tp @ Wp, Tm @ Wm
-    out = np.zeros((o, o, v, v))
+    return Tp, Tm
+
+
+def sa_pack_vvvv(W4slab, v, b0):
+    """[W+ | W-] for the column block of z in [b0, b0+vs) from the slab W4slab[e,f,w,z-b0] = <ef|wz>."""
+    vs = W4slab.shape[3]
+    hv = v // 2 + 1
+    pairs = [(e, f) for e in range(v) for f in range(e + 1)]
+    Wp, Wm = np.zeros((len(pairs), vs * hv)), np.zeros((len(pairs), vs * hv))
+    for zl in range(vs):
+        z = b0 + zl
+        for t in range(hv):
+            w = sa_partner(z, t, v)
+            if w < 0:
+                continue
+            for P, (e, f) in enumerate(pairs):
+                x, y = W4slab[e, f, w, zl], W4slab[f, e, w, zl]
+                Wp[P, zl * hv + t] = 2 * x if e == f else x + y
+                Wm[P, zl * hv + t] = x - y if w > z else y - x
+    return Wp, Wm
+
+
+def sa_unpack(Lp, Lm, o, v, b0, vs):
+    out = np.zeros((o, o, v, vs))
     for a in range(v):
-        for b in range(v):
-            hi, lo = max(a, b), min(a, b)
-            Q = hi * (hi + 1) // 2 + lo
+        for bl in range(vs):
+            b = b0 + bl
+            Q = sa_column(a, b, v)
             s = 0.5 if a > b else (-0.5 if a < b else 0.0)
-            out[:, :, a, b] = (0.5 * Lp[:, Q] + s * Lm[:, Q]).reshape(o, o, order="F")
+            out[:, :, a, bl] = (0.5 * Lp[:, Q] + s * Lm[:, Q]).reshape(o, o, order="F")
     return out
+
+
+def sa_ladder(tau, W4, nranks=1):
+    """sum_ef tau[i,j,e,f] W4[e,f,a,b] (W4[e,f,a,b] = <ef|ab> = W4[f,e,b,a]) as the device does it:
+    per rank two (o^2 x np)(np x nq) products over its block of the output pairs, all-gather of the
+    blocks, unpack of the rank's slab; returns the full (o,o,v,v) result assembled from the slabs."""
+    o, v = tau.shape[0], tau.shape[2]
+    assert v % (2 * nranks) == 0
+    vs = v // nranks
+    Tp, Tm = sa_pack_tau(tau)
+    Lp_blocks, Lm_blocks = [], []
+    for r in range(nranks):
+        Wp, Wm = sa_pack_vvvv(W4[:, :, :, r * vs:(r + 1) * vs], v, r * vs)
+        Lp_blocks.append(Tp @ Wp)
+        Lm_blocks.append(Tm @ Wm)
+    Lp, Lm = np.concatenate(Lp_blocks, axis=1), np.concatenate(Lm_blocks, axis=1)      # all-gather
+    return np.concatenate([sa_unpack(Lp, Lm, o, v, r * vs, vs) for r in range(nranks)], axis=3)

@@ -8,6 +8,7 @@ slabs S_r; rank r holds only the last-index slabs of the v^4 and ov^3 integral c
     W4[e,f,a,b] = <ef|ab>,  OA[e,f,m,b] = <ef|mb> = ovvv[m,b,e,f],  OB[a,j,e,b] = <aj|eb> = (ae|jb)
 for b in S_r, builds every ring intermediate only for its slab, and exchanges
     * one sum-all-reduce of the small partial intermediates (Fae, Fmi, Wpp, R1),
+    * one all-gather of the packed ladder blocks [L+ | L-] (o^2 v^2 doubles in total),
     * one all-gather of the half residual H' (o^2 v^2 in total),
     * one all-gather of the new T2 slab.
 `comm` supplies allreduce(array)->array and allgather_last(array)->array (concatenate along the
@@ -120,7 +121,14 @@ def sweep(R, t, T, eo, ev, b0, b1, comm=None, singles=True, fock=None):
         WJ -= 0.5 * es("mnef,jnfb->mejb", V, T[..., S])
         WE += 0.5 * es("nmef,jnfb->mejb", V, T[..., S])
     # ---- ladders and half residual for the slab -----------------------------------------------------
-    Lpp = es("ijef,efab->ijab", tau, W4)
+    # particle-particle ladder through the packed symmetric/antisymmetric pair space: this rank's block of
+    # the output pairs, all-gather of the blocks, unpack of the rank's slab (cc.cu: sa_ladder)
+    import factorized_model as fm
+    Tp, Tm = fm.sa_pack_tau(tau)
+    Wp, Wm = fm.sa_pack_vvvv(W4, v, b0)        # static in the library (built once)
+    Lp = comm.allgather_last(Tp @ Wp)
+    Lm = comm.allgather_last(Tm @ Wm)
+    Lpp = fm.sa_unpack(Lp, Lm, o, v, b0, b1 - b0)
     Lhh = es("mnij,mnab->ijab", Wpp, tau[..., S])
     H = es("ijae,eb->ijab", T, FaeT_t[:, S]) - es("imab,mj->ijab", T[..., S], Fmi_t)
     H += es("imae,mejb->ijab", Tt, WJ) + es("imae,mejb->ijab", T, WE)

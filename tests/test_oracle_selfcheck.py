@@ -129,16 +129,35 @@ def test_flop_model_matches_the_survey_table():
 
 
 def test_symmetric_antisymmetric_ladder_identity():
-    """The packed-pair pp-ladder the device executes on one rank == the plain tau.vvvv contraction."""
+    """The packed-pair pp-ladder the device executes (tests/factorized_model.py mirrors the kernels'
+    index functions) == the plain tau.vvvv contraction, for 1, 2 and 3 ranks' column blocks."""
     import numpy as np
     import factorized_model as fm
     from jues.jl_b200 import synth
     from oracle import jues_oracle as orc
-    g, Cao, Cav, eps = synth.dense_inputs(9, 3, seed=4)
-    I = fm.unique_integrals(g, Cao, Cav)
-    w = orc.Wfn(3, 6, eps, Cao, Cav, g)
-    e, T1, T2 = orc.do_rccsd(w, maxit=2, return_T=True)
-    tau = T2 + np.einsum("ia,jb->ijab", T1, T1)
-    W4 = np.ascontiguousarray(I["vvvv"].transpose(2, 3, 0, 1))       # W4[e,f,a,b] = <ef|ab> = vvvv[a,b,e,f]
-    ref = np.einsum("ijef,efab->ijab", tau, W4)
-    assert np.abs(fm.sa_ladder(tau, W4) - ref).max() < 1e-14 * max(1.0, np.abs(ref).max())
+    for (N, o, nr) in [(9, 3, 1), (11, 3, 2), (10, 4, 3), (5, 3, 1)]:
+        g, Cao, Cav, eps = synth.dense_inputs(N, o, seed=4)
+        I = fm.unique_integrals(g, Cao, Cav)
+        w = orc.Wfn(o, N - o, eps, Cao, Cav, g)
+        e, T1, T2 = orc.do_rccsd(w, maxit=2, return_T=True)
+        tau = T2 + np.einsum("ia,jb->ijab", T1, T1)
+        W4 = np.ascontiguousarray(I["vvvv"].transpose(2, 3, 0, 1))   # W4[e,f,a,b] = <ef|ab> = vvvv[a,b,e,f]
+        v = N - o
+        vp = -(-v // (2 * nr)) * (2 * nr)                            # padded like the device
+        taup = np.pad(tau, [(0, 0), (0, 0), (0, vp - v), (0, vp - v)])
+        W4p = np.pad(W4, [(0, vp - v)] * 4)
+        ref = np.einsum("ijef,efab->ijab", taup, W4p)
+        got = fm.sa_ladder(taup, W4p, nranks=nr)
+        assert np.abs(got - ref).max() < 1e-14 * max(1.0, np.abs(ref).max()), (N, o, nr)
+    # every unordered pair has exactly one column, pad slots excepted
+    for v in (2, 4, 6, 10):
+        cols = {}
+        for a in range(v):
+            for b in range(a + 1):
+                cols.setdefault(fm.sa_column(a, b, v), []).append((a, b))
+        assert all(len(x) == 1 for x in cols.values()) and max(cols) < v * (v // 2 + 1)
+        for z in range(v):
+            for t in range(v // 2 + 1):
+                w = fm.sa_partner(z, t, v)
+                if w >= 0:
+                    assert fm.sa_column(z, w, v) == z * (v // 2 + 1) + t
