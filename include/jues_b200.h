@@ -227,6 +227,14 @@ int jues_b200_get_counters(jues_ctx* ctx, double* gemm_flops, int64_t* gemm_laun
                            int64_t* aux_launches, int64_t* bytes_peak);
 /* NCCL collectives issued by the last call and the bytes this rank received in them.           */
 int jues_b200_get_comm_counters(jues_ctx* ctx, int64_t* collectives, double* bytes_received);
+/* Kernel-level check of the packed (symmetric/antisymmetric) particle-particle ladder, the largest
+ * contraction of the sweeps (form_T2 term T2[i,j,e,f]*Wabef, RCCD.jl:247; RCCSD.jl:268):
+ * out[i,j,a,b] = sum_ef tau[i,j,e,f] W4[e,f,a,b] for W4[e,f,a,b] = <ef|ab> (= W4[f,e,b,a]), evaluated
+ * exactly as `nslabs` ranks would: per slab of the last index its own [W+|W-] block, one batched GEMM,
+ * the blocks side by side instead of all-gathered, every slab unpacked.  tau (nocc,nocc,nvir,nvir),
+ * W4 (nvir,nvir,nvir,nvir), out (nocc,nocc,nvir,nvir): host.                                   */
+int jues_b200_sa_ladder(jues_ctx* ctx, const double* tau, const double* W4, int64_t nocc, int64_t nvir,
+                        int nslabs, double* out);
 /* Time `reps` back-to-back launches of the DGEMM kernel on device-resident random operands
  * (no host traffic); returns average ms per launch.  Used for the roofline line.            */
 int jues_b200_dgemm_bench(jues_ctx* ctx, char transA, char transB, int64_t M, int64_t N, int64_t K,

@@ -237,6 +237,17 @@ class Context:
                                               _p(Cm), max(M, 1)))
         return Cm
 
+    def sa_ladder(self, tau, W4, nslabs: int = 1) -> np.ndarray:
+        """sum_ef tau[i,j,e,f] W4[e,f,a,b] through the packed symmetric/antisymmetric pair space, evaluated
+        as `nslabs` ranks of the coupled-cluster driver would (kernel-level check, jues_b200_sa_ladder)."""
+        tau = _f(tau)
+        o, _, v, _ = tau.shape
+        tau = _f(tau, (o, o, v, v))
+        W4 = _f(W4, (v, v, v, v))
+        out = np.empty((o, o, v, v), order="F")
+        self._check(self._lib.jues_b200_sa_ladder(self._h, _p(tau), _p(W4), o, v, int(nslabs), _p(out)))
+        return out
+
     def gemm_bench(self, tA: str, tB: str, M: int, N: int, K: int, reps: int = 3) -> float:
         ms = C.c_double()
         self._check(self._lib.jues_b200_dgemm_bench(self._h, tA.encode(), tB.encode(), M, N, K, reps,

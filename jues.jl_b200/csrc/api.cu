@@ -651,3 +651,45 @@ extern "C" int jues_b200_mrccd_t4(jues_ctx* ctx, const jues_t4* gao, const doubl
     run_mrccd(ctx, *holder.src, Cao, nocc, Cav, nvir, eps, maxit, e_ccd, iterations, rms_hist, e_hist, T2_out);
     JUES_API_END(ctx)
 }
+
+// ---------------------------------------------------------------------------------------------
+// Kernel-level check of the packed (symmetric / antisymmetric) particle-particle ladder
+// ---------------------------------------------------------------------------------------------
+#include "dgemm.h"
+
+// out[i,j,a,b] = sum_ef tau[i,j,e,f] W4[e,f,a,b] evaluated exactly as `nslabs` ranks of the CC driver
+// would (cc.cu: sa_ladder): per slab of the last index pack [W+|W-] from that slab only, one batched
+// GEMM into the slab's column block of [L+|L-], then -- all blocks being in one buffer here instead of
+// all-gathered -- unpack every slab.  Lets a single GPU exercise the b0 != 0 code paths of the kernels.
+extern "C" int jues_b200_sa_ladder(jues_ctx* ctx, const double* tau, const double* W4, int64_t nocc,
+                                   int64_t nvir, int nslabs, double* out) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    JUES_REQUIRE(tau && W4 && out, "null argument");
+    JUES_REQUIRE(nocc > 0 && nvir > 0 && nslabs >= 1 && nslabs <= 64, "bad extents / slab count");
+    const int64_t o = round_up(nocc, 2), v = round_up(nvir, 2 * (int64_t)nslabs), vs = v / nslabs;
+    const int64_t oo = o * o, np = sa_pairs(v), ld = round_up(np, 2), nq = vs * sa_slots(v), nq_all = v * sa_slots(v);
+    DTen taud, W4d;
+    const int64_t dt[4] = {nocc, nocc, nvir, nvir}, pt[4] = {o, o, v, v};
+    upload_padded_t4(ctx, taud, tau, dt, pt);
+    const int64_t dw[4] = {nvir, nvir, nvir, nvir}, pw[4] = {v, v, v, v};
+    upload_padded_t4(ctx, W4d, W4, dw, pw);
+    DBuf Tpm(ctx, (size_t)(2 * oo * ld)), Lpm(ctx, (size_t)(2 * oo * nq_all)), outd(ctx, (size_t)(oo * v * v));
+    pack_tau_sa(ctx, taud.p(), oo, v, ld, Tpm.p);
+    for (int64_t r = 0; r < nslabs; ++r) {
+        DBuf Wsa(ctx, (size_t)(2 * ld * nq));
+        Wsa.zero();
+        // the slab W4[e,f,w,z in S_r] is a contiguous block (last index slowest)
+        pack_vvvv_sa(ctx, W4d.p() + v * v * v * (r * vs), v, r * vs, vs, ld, Wsa.p);
+        GemmCall g;
+        g.M = oo; g.N = nq; g.K = np; g.batch = 2;
+        g.A = Tpm.p; g.lda = oo; g.strideA = oo * ld;
+        g.B = Wsa.p; g.ldb = ld; g.strideB = ld * nq;
+        g.C = Lpm.p + oo * nq * r; g.ldc = oo; g.strideC = oo * nq_all;
+        dgemm(ctx, g);
+    }
+    for (int64_t r = 0; r < nslabs; ++r)
+        unpack_ladder_sa(ctx, Lpm.p, oo, v, r * vs, vs, outd.p + oo * v * (r * vs));
+    download_block(ctx, outd.p, pt, out, dt);
+    JUES_API_END(ctx)
+}
