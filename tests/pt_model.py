@@ -64,7 +64,9 @@ def X_block(Dv, p, q, r):
     return x_blocks(Dv, p, 0, q, 0, r, 1, 1)[0]
 
 
-def pt_energy(Dv, fo, fv, nocc=None):
+def pt_energy(Dv, fo, fv, nocc=None, rank=0, nranks=1):
+    """This rank's share of E(T): occupied pairs (i >= j) are dealt round-robin (pt.cu); the shares are
+    summed over ranks by the caller."""
     t, Vv = Dv["t"], Dv["Vv"]
     o, v = t.shape
     nocc = o if nocc is None else nocc
@@ -73,8 +75,12 @@ def pt_energy(Dv, fo, fv, nocc=None):
     wab = 1.0 / (1.0 + (a_ == b_) + (b_ == c_))
     fvs = fv[:, None, None] + fv[None, :, None] + fv[None, None, :]
     slots = []
+    pair = -1
     for i in range(nocc):
         for j in range(i + 1):
+            pair += 1
+            if pair % nranks != rank:
+                continue
             # one batch over k = 0..j (the device chunks it when memory is short): six launches
             nb = j + 1
             F1, F2 = x_blocks(Dv, i, 0, j, 0, 0, 1, nb), x_blocks(Dv, i, 0, 0, 1, j, 0, nb)

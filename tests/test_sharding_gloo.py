@@ -138,3 +138,70 @@ def test_sharded_sweep_over_gloo(world, singles):
         p.join(timeout=180)
         assert p.exitcode == 0
     assert q.get(timeout=5) < 1e-13
+
+
+def _auto_worker(rank, world, port, N, o, seed, q):
+    """AutoRCCSD on `world` ranks: sharded sweeps with the replicated one-body Fock terms, then the (T)
+    correction with the occupied pairs dealt to the ranks and a scalar all-reduce."""
+    import torch
+    import torch.distributed as dist
+    import pt_model as pm
+    from oracle import jues_oracle_auto as oa
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class Comm:
+            def allreduce(self, x):
+                t_ = torch.from_numpy(np.ascontiguousarray(x))
+                dist.all_reduce(t_)
+                return t_.numpy()
+
+            def allgather_last(self, x):
+                xs = np.ascontiguousarray(np.moveaxis(x, -1, 0))
+                parts = [torch.empty(xs.shape, dtype=torch.float64) for _ in range(world)]
+                dist.all_gather(parts, torch.from_numpy(xs))
+                return np.moveaxis(np.concatenate([p.numpy() for p in parts], axis=0), 0, -1)
+
+        g, h, Ca, eps = jb.synth.noncanonical_inputs(N, o, seed=seed, ov_mix=0.02)
+        v = N - o
+        w = orc.Wfn(o, v, eps, Ca[:, :o].copy(), Ca[:, o:].copy(), g, hao=h, Ca=Ca)
+        f, V, d, D, fo, fv = oa.auto_setup(w)
+        I6 = fm.unique_integrals(g, w.Cao, w.Cav)
+        vp, b0, b1 = sm.slab_bounds(v, world, rank)
+        R = sm.rank_integrals(sm.pad_virtuals(I6, v, vp), b0, b1)
+        pad = lambda x, ax: np.pad(x, [(0, vp - v) if k in ax else (0, 0) for k in range(x.ndim)])
+        fp = (f[0], pad(f[1], (1,)), pad(f[2], (0, 1)))
+        evp = np.concatenate([fv, np.full(vp - v, fv.max() + 1e3)])
+        t, T = pad(f[1] / d, (1,)), pad(V[2] / D, (2, 3))
+        T1, T2 = f[1] / d, V[2] / D
+        for _ in range(3):
+            t, T = sm.sweep(R, t, T, fo, evp, b0, b1, comm=Comm(), singles=True, fock=fp)
+            T1, T2, _, _ = oa.auto_update_amp(T1, T2, f, V, d, D)
+        err = max(np.abs(t[:, :v] - T1).max(), np.abs(T[:, :, :v, :v] - T2).max())
+        # (T): every rank holds the gathered operands; pairs dealt round-robin, scalar all-reduce
+        Dv = pm.device_tensors(t, T, pad(V[4], (1, 2, 3)), pad(V[1], (3,)), pad(V[2], (2, 3)))
+        share = np.array([pm.pt_energy(Dv, fo, evp, rank=rank, nranks=world)])
+        ept = float(Comm().allreduce(share)[0])
+        ref = oa.compute_pT(T1=T1, T2=T2, Vvvvo=V[4].transpose(3, 1, 2, 0), Vvooo=V[1].transpose(3, 1, 0, 2),
+                            Vvovo=V[2].transpose(2, 0, 3, 1), fo=fo, fv=fv)
+        if rank == 0:
+            q.put((float(err), abs(ept - ref), abs(ref)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_auto_rccsd_and_triples_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_auto_worker, args=(r, world, port, 9, 3, 13, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    err, dpt, mag = q.get(timeout=5)
+    assert err < 1e-13 and dpt < 1e-14 and mag > 1e-8
