@@ -295,8 +295,10 @@ struct CC {
             if (t->p()) pcache.add(t->t, false);
     }
     ~CC() {
+        bool had_graph = false;
         for (auto& g : graphs)
-            if (g.exec) cudaGraphExecDestroy(g.exec);
+            if (g.exec) { cudaGraphExecDestroy(g.exec); had_graph = true; }
+        if (had_graph) cudaDeviceGraphMemTrim(ctx->device);   // give the graphs' memory back to the device
         ctx->perm_cache = nullptr;
         pcache.clear();
     }
@@ -729,7 +731,11 @@ AutoResult auto_rccsd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, const doubl
     // memory; `done[k%2]` fires when they have landed.
     DBuf sc2(ctx, 8);
     double* hp = ctx->red_host + 8;                    // pinned landing zone: 2 x 3 doubles
-    cudaEvent_t done[2];
+    struct Events {                                    // destroyed on every exit path
+        cudaEvent_t e[2] = {nullptr, nullptr};
+        ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); }
+        cudaEvent_t& operator[](int k) { return e[k]; }
+    } done;
     JUES_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
     JUES_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     auto enqueue = [&](int k) {
@@ -778,8 +784,6 @@ AutoResult auto_rccsd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, const doubl
         ctx->timings.emplace_back("cc.speculative_sweeps", 1.0f);
     }
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaEventDestroy(done[0]);
-    cudaEventDestroy(done[1]);
     ctx->timings.emplace_back("cc.graph_launches", (float)ctx->stats.graph_launches);
     res.iterations = ite - 1;
     res.converged = std::fabs(dE) < opt.e_conv && rms < opt.max_rms;          // :288
