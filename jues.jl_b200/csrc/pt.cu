@@ -208,7 +208,10 @@ double pt_dev(jues_ctx* ctx, const PtInputs& in, double* scratch, size_t scratch
         kbmax = (int64_t)(0.6 * (double)free_b / (8.0 * 8.0 * (double)v3));
         kbmax = std::max<int64_t>(1, std::min<int64_t>(kbmax, nocc));
     }
-    if (getenv("JUES_B200_PT_KB")) kbmax = std::max(1, atoi(getenv("JUES_B200_PT_KB")));   // testing hook
+    if (getenv("JUES_B200_PT_KB")) {                                                       // testing hook
+        const int64_t kb_env = std::max(1, atoi(getenv("JUES_B200_PT_KB")));
+        kbmax = base ? std::min(kbmax, kb_env) : kb_env;      // never beyond what the scratch block holds
+    }
     if (!base) {
         TraceTimer tal(ctx, "pt.alloc");
         work.alloc(ctx, (size_t)(8 * kbmax * v3));
