@@ -19,6 +19,8 @@ CPU".  One JSON line is printed by rank 0:
     peak of this pool (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json records no FP64 figure).
   * `cpu_baseline` is the oracle (numpy restatement of the reference's literal algorithm, "port")
     timed on this box's host cores on a bounded sample.
+  * `next_rows` (extra, N=1 only): AutoRCCSD.do_rccsd with the (T) correction on the same inputs through
+    the C ABI from host buffers -- sweeps to convergence, Fock build and (T) times.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port; there is no Julia here)
 on the same config and prints the same line shape.
@@ -399,6 +401,33 @@ def gpu_arm(args, rank, world):
                "sample": f"oracle (numpy/OpenBLAS port of the reference's literal algorithm): 15 transforms "
                          f"({t_tr:.1f} s) + 1 sweep ({t_it:.1f} s) at nbf={NBF} nocc={NOCC}",
                "energy_check": abs(e_cpu - hist[1]) if len(hist) > 1 else None}
+    # ---- the callers either side of the path, same inputs, one GPU: AutoRCCSD to
+    #      |dE|, rms <= 1e-10 with the (T) correction, through the C ABI from host buffers.  Extra keys only;
+    #      never allowed to break the line.
+    next_rows = None
+    if world == 1 and not args.no_next_rows:
+        try:
+            from importlib import import_module
+            fl = import_module("jues.jl_b200.flops")
+            t0 = time.perf_counter()
+            hao = jb.synth.core_hamiltonian(g, Cao, Cav, eps)      # host plumbing: makes (C, eps) the RHF solution
+            t_h = time.perf_counter() - t0
+            wa = jb.Wfn(NOCC, v, eps, Cao, Cav, g, hao=hao)
+            t0 = time.perf_counter()
+            r = jb.AutoRCCSD.do_rccsd(wa, ctx=ctx, do_pT=True, _return_all=True)
+            t_auto = time.perf_counter() - t0
+            pa = ctx.phases()
+            sw = [ms for k, ms in pa if k == "cc.iteration"]
+            tr = [ms for k, ms in pa if k == "cc.triples"]
+            next_rows = {"what": "AutoRCCSD.do_rccsd(do_pT=true) from host buffers: get_fock + transform + sweeps to "
+                                 "1e-10 + (T)", "s_per_call": t_auto, "host_core_hamiltonian_s": t_h,
+                         "iterations": r["iterations"], "converged": r["converged"], "e_ccsd": r["ecc"], "e_pt": r["ept"],
+                         "ms_per_sweep_median": float(np.median(sw)) if sw else None,
+                         "fock_build_ms": [ms for k, ms in pa if k == "fock.build"],
+                         "triples_ms": tr[0] if tr else None,
+                         "triples_tflops": fl.pt_flops(NOCC, v) / (tr[0] * 1e-3) * 1e-12 if tr else None}
+        except Exception as ex:     # noqa: BLE001
+            next_rows = {"error": str(ex)[:300]}
     F_alg = flops_alg_rccsd(o, v)
     line = {
         # algorithmic FP64 throughput: F_alg per sweep / seconds per sweep (both arms use F_alg);
@@ -435,6 +464,7 @@ def gpu_arm(args, rank, world):
         "clocks": clocks,
         "energy": {"E_ccsd_after_timed_sweeps": e, "E_ccsd_40_sweeps_e2e": e_host},
         "integral_transform_ms": tr_ms,
+        "next_rows": next_rows,
     }
     print(json.dumps(line), flush=True)
 
@@ -446,6 +476,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the AutoRCCSD(T) extra keys")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
