@@ -240,6 +240,22 @@ int jues_b200_sa_ladder(jues_ctx* ctx, const double* tau, const double* W4, int6
 int jues_b200_dgemm_bench(jues_ctx* ctx, char transA, char transB, int64_t M, int64_t N, int64_t K,
                           int reps, double* ms_avg);
 
+/* Determinism stress of the DGEMM kernel: the product is launched reps+1 times on device-resident
+ * pseudo-random operands and every repetition compared with the first ON THE DEVICE; *n_bad = number of
+ * repetitions that differ (0 expected), *worst_sqdiff = largest sum of squared differences.  batch > 1:
+ * the quarter-transform layout A[M,K,batch], B shared, C[M,N,batch] ('N','N').                */
+int jues_b200_dgemm_stress(jues_ctx* ctx, char transA, char transB, int64_t M, int64_t N, int64_t K,
+                           int64_t batch, int reps, int* n_bad, double* worst_sqdiff);
+
+/* Determinism stress of the 4-index transform (test hook): reps+1 identical transforms inside one call,
+ * the output of each of the four quarter transforms compared on the device with the first run's.
+ * stats[reps][4 quarters][4] = {elements that differ (0 expected), first and last differing linear index
+ * (-1: none), largest |difference|} per repetition and quarter (in execution order).           */
+int jues_b200_transform_stress(jues_ctx* ctx, const jues_t4* gao,
+                               const double* C1, int64_t d1, const double* C2, int64_t d2,
+                               const double* C3, int64_t d3, const double* C4, int64_t d4,
+                               int reps, double* stats);
+
 #ifdef __cplusplus
 }
 #endif

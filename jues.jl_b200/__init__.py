@@ -255,6 +255,14 @@ class Context:
         return ms.value
 
 
+    def gemm_stress(self, tA: str, tB: str, M: int, N: int, K: int, batch: int = 1, reps: int = 20):
+        """(repetitions that differ from the first launch, worst sum of squared differences): 0, 0.0 expected."""
+        nb, w = C.c_int(), C.c_double()
+        self._check(self._lib.jues_b200_dgemm_stress(self._h, tA.encode(), tB.encode(), M, N, K, batch, reps,
+                                                     C.byref(nb), C.byref(w)))
+        return nb.value, w.value
+
+
 def slab_bounds(nvir: int, nranks: int, rank: int):
     """Host-side mirror of the library's partition of the virtual index over ranks
     (csrc/cc.cu: setup_problem + dist.h: slab_of): nvir is padded to a multiple of 2*nranks and

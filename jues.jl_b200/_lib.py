@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjues_b200.so")
+LIB_PATH = os.environ.get("JUES_B200_LIB") or os.path.join(_HERE, "libjues_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
@@ -100,6 +100,10 @@ SIGNATURES = {
     "jues_b200_get_counters": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_int64_p, c_int64_p]),
     "jues_b200_dgemm_bench": (C.c_int, [C.c_void_p, C.c_char, C.c_char, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_int, c_double_p]),
+    "jues_b200_transform_stress": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int64, c_double_p, C.c_int64,
+                                             c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int, c_double_p]),
+    "jues_b200_dgemm_stress": (C.c_int, [C.c_void_p, C.c_char, C.c_char, C.c_int64, C.c_int64, C.c_int64,
+                                         C.c_int64, C.c_int, C.POINTER(C.c_int), c_double_p]),
 }
 
 _lib = None

@@ -173,6 +173,81 @@ extern "C" int jues_b200_tei_transform_t4(jues_ctx* ctx, const jues_t4* gao, con
     JUES_API_END(ctx)
 }
 
+// Determinism stress of the transform (test hook): the same transform is run reps+1 times inside one call;
+// the output of every quarter of every repetition is compared on the device with the first run's.
+// bad[4] / worst[4]: per quarter, repetitions that differ and the largest sum of squared differences.
+namespace {
+struct ProbeState {
+    DBuf ref[4];
+    DBuf res;     // per (rep, quarter): [count, first index, last index, max |diff|]
+    int rep = -1, reps = 0;
+};
+__global__ void diffstat_kernel(const double* __restrict__ a, const double* __restrict__ b, size_t n,
+                                double* __restrict__ out) {
+    unsigned long long cnt = 0, first = ~0ull, last = 0;
+    double mx = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double d = fabs(a[i] - b[i]);
+        if (d != 0.0 || a[i] != a[i] || b[i] != b[i]) {
+            ++cnt;
+            if (i < first) first = i;
+            if (i > last) last = i;
+            if (d > mx) mx = d;
+        }
+    }
+    if (cnt) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(out), cnt);
+        atomicMin(reinterpret_cast<unsigned long long*>(out + 1), first);
+        atomicMax(reinterpret_cast<unsigned long long*>(out + 2), last);
+        atomicMax(reinterpret_cast<unsigned long long*>(out + 3), (unsigned long long)__double_as_longlong(mx));
+    }
+}
+void stress_probe(void* user, jues_ctx* ctx, int step, const double* out, size_t n) {
+    ProbeState* st = static_cast<ProbeState*>(user);
+    if (st->rep < 0) {
+        st->ref[step].alloc(ctx, n);
+        cudaMemcpyAsync(st->ref[step].p, out, n * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    } else {
+        diffstat_kernel<<<148 * 8, 256, 0, ctx->stream>>>(st->ref[step].p, out, n, st->res.p + 4 * (4 * st->rep + step));
+    }
+}
+}  // namespace
+
+extern "C" int jues_b200_transform_stress(jues_ctx* ctx, const jues_t4* gao, const double* C1, int64_t d1,
+                                          const double* C2, int64_t d2, const double* C3, int64_t d3,
+                                          const double* C4, int64_t d4, int reps, double* stats) {
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    check_t4_is_gao(gao);
+    JUES_REQUIRE(reps > 0 && reps <= 1024 && stats, "bad arguments");
+    T4Source holder(gao);
+    const double* Ch[4] = {C1, C2, C3, C4};
+    const int64_t d[4] = {d1, d2, d3, d4};
+    ProbeState st;
+    st.reps = reps;
+    st.res.alloc(ctx, (size_t)reps * 16);
+    std::vector<unsigned long long> init((size_t)reps * 16, 0ull);
+    for (int k = 0; k < reps * 4; ++k) init[(size_t)4 * k + 1] = ~0ull;
+    JUES_CUDA(cudaMemcpyAsync(st.res.p, init.data(), init.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    struct Guard { ~Guard() { set_quarter_probe(nullptr, nullptr); } } guard;
+    set_quarter_probe(stress_probe, &st);
+    for (int r = -1; r < reps; ++r) {
+        st.rep = r;
+        DBuf res;
+        int64_t dp[4];
+        transform_common(ctx, *holder.src, Ch, d, 0, res, dp);
+    }
+    std::vector<unsigned long long> h((size_t)reps * 16);
+    JUES_CUDA(cudaMemcpyAsync(h.data(), st.res.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < h.size(); ++k) {
+        if (k % 4 == 3) { double x; memcpy(&x, &h[k], 8); stats[k] = x; }
+        else stats[k] = (h[k] == ~0ull) ? -1.0 : (double)h[k];
+    }
+    JUES_API_END(ctx)
+}
+
 // ---------------------------------------------------------------------------------------------
 // RMP2
 // ---------------------------------------------------------------------------------------------

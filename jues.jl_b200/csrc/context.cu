@@ -2,6 +2,7 @@
 #include "jues_common.h"
 #include "dgemm.h"
 #include "api_util.h"
+#include "tensor_ops.h"
 
 #include <mutex>
 
@@ -40,6 +41,8 @@ extern "C" int jues_b200_init(jues_ctx** out, int device) {
         ctx = new jues_ctx();
         ctx->device = device;
         ctx->sm_count = prop.multiProcessorCount;
+        if (const char* mb = getenv("JUES_B200_BIG_MB")) ctx->big_bytes = (size_t)std::max(1, atoi(mb)) << 20;
+        ctx->sync_comm = getenv("JUES_B200_SYNC_COMM") != nullptr;
         JUES_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         {   // keep freed blocks in the stream-ordered pool (all work of a context is on one stream)
             cudaMemPool_t pool;
@@ -196,5 +199,50 @@ extern "C" int jues_b200_dgemm_bench(jues_ctx* ctx, char transA, char transB, in
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *ms_avg = ms / reps;
+    JUES_API_END(ctx)
+}
+
+// Determinism / self-consistency stress of the DGEMM kernel at a given shape: the same product is
+// launched `reps`+1 times on device-resident pseudo-random operands; every repetition is compared with
+// the first on the device (sum of squared differences, exact 0 expected).  batch > 1 uses the layout
+// of the quarter transforms (A [M,K,batch], B shared, C [M,N,batch]).
+extern "C" int jues_b200_dgemm_stress(jues_ctx* ctx, char transA, char transB, int64_t M, int64_t N,
+                                      int64_t K, int64_t batch, int reps, int* n_bad, double* worst_sqdiff) {
+    JUES_API_BEGIN(ctx)
+    const bool tA = (transA == 'T' || transA == 't');
+    const bool tB = (transB == 'T' || transB == 't');
+    JUES_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && reps > 0 && reps <= 4096 && n_bad && worst_sqdiff,
+                 "bad arguments");
+    JUES_REQUIRE(batch == 1 || (!tA && !tB && (M & 1) == 0), "batched stress: 'N','N' with even M only");
+    const int64_t ar = round_up(tA ? K : M, 2), ac = tA ? M : K;
+    const int64_t br = round_up(tB ? N : K, 2), bc = tB ? K : N;
+    const int64_t lc = round_up(M, 2);
+    DBuf dA(ctx, (size_t)ar * ac * batch), dB(ctx, (size_t)br * bc), dC0(ctx, (size_t)lc * N * batch),
+        dC1(ctx, (size_t)lc * N * batch), res(ctx, (size_t)reps);
+    fill_pattern(ctx, dA.p, dA.n, 1);
+    fill_pattern(ctx, dB.p, dB.n, 2);
+    GemmCall g;
+    g.transA = tA; g.transB = tB;
+    g.M = M; g.N = N; g.K = K; g.batch = batch;
+    g.A = dA.p; g.lda = ar; g.strideA = ar * ac;
+    g.B = dB.p; g.ldb = br; g.strideB = 0;
+    g.C = dC0.p; g.ldc = lc; g.strideC = lc * N;
+    g.force_cfg = ctx_force_cfg(ctx);
+    dC0.zero();
+    dgemm(ctx, g);
+    g.C = dC1.p;
+    for (int r = 0; r < reps; ++r) {
+        dC1.zero();
+        dgemm(ctx, g);
+        sqdiff_async(ctx, dC0.n, dC0.p, dC1.p, res.p + r);
+    }
+    std::vector<double> h((size_t)reps);
+    JUES_CUDA(cudaMemcpyAsync(h.data(), res.p, (size_t)reps * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_bad = 0; *worst_sqdiff = 0.0;
+    for (double x : h) {
+        if (x != 0.0) ++*n_bad;
+        if (x > *worst_sqdiff || x != x) *worst_sqdiff = x;
+    }
     JUES_API_END(ctx)
 }

@@ -250,10 +250,25 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+        // Release protocol.  A stage may go back to the TMA producer only when every LDS that reads it
+        // has RETURNED its data.  Neither `asm volatile` nor the release semantics of mbarrier.arrive
+        // make ptxas keep the DMMAs (which are what waits for the loaded registers) in front of the
+        // arrive: it sinks them below it, so an arrive at the end of the k-step is issued right behind
+        // the youngest LDS of the stage.  Measured on B200 (profiles/gemm_release_race_r02.md): those
+        // youngest loads then occasionally return the NEXT fill of the stage -- 8x16 blocks of C wrong in
+        // ~1 of 10^4 tiles on a cold GPU.  So the arrive for stage s is issued at the top of the NEXT
+        // k-step, behind the spin-wait on the next full barrier: a control-flow boundary the DMMAs of
+        // step s cannot cross, and by then they have all issued, i.e. consumed every loaded register.
+        int s_prev = -1;
         for (int kt = 0; kt < KT; ++kt, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (uint32_t)((it / STAGES) & 1);
             mbar_wait(bar_full + 8 * s, ph);
+            if (s_prev >= 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_empty + 8 * s_prev);
+            }
+            s_prev = s;
             const uint32_t st = smem_base + s * L::STAGE_BYTES;
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
@@ -272,8 +287,6 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         }
 
         // ================================= epilogue of this tile ================================
@@ -296,6 +309,12 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     }
                 }
             }
+        }
+        // the last stage of the tile: its loads are certainly consumed once the accumulators have been
+        // stored (the stores depend on every DMMA, and the arrive cannot move above them: "memory" clobber)
+        if (s_prev >= 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s_prev);
         }
     }
 }

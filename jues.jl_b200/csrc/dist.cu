@@ -67,18 +67,22 @@ void dist_teardown(jues_ctx* ctx) {
 
 void all_gather_inplace(jues_ctx* ctx, double* full, size_t count_per_rank) {
     if (ctx->nranks == 1) return;
+    if (ctx->sync_comm) JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     // rank r's slab already sits at full + r*count_per_rank (in-place all-gather)
     nccl_check(g_nccl.AllGather(full + (size_t)ctx->rank * count_per_rank, full, count_per_rank, ncclDouble,
                                 (ncclComm_t)ctx->nccl_comm, ctx->stream),
                "ncclAllGather");
+    if (ctx->sync_comm) JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stats.collectives++;
     ctx->stats.collective_bytes += (double)count_per_rank * 8.0 * (ctx->nranks - 1);
 }
 
 void all_reduce_sum(jues_ctx* ctx, double* buf, size_t count) {
     if (ctx->nranks == 1) return;
+    if (ctx->sync_comm) JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     nccl_check(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream),
                "ncclAllReduce");
+    if (ctx->sync_comm) JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stats.collectives++;
     ctx->stats.collective_bytes += (double)count * 8.0;
 }

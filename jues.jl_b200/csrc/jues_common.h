@@ -97,6 +97,10 @@ struct jues_ctx {
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
     void* perm_cache = nullptr;   // jues::PermCache of the running calculation (contract.h)
+    // diagnostics (environment, read once in jues_b200_init): JUES_B200_BIG_MB moves the pool / cudaMalloc
+    // threshold of DBuf, JUES_B200_SYNC_COMM=1 drains the stream around every collective
+    size_t big_bytes = size_t(64) << 20;
+    bool sync_comm = false;
     // per-sweep amplitude capture (tests)
     jues_b200_amp_cb amp_cb = nullptr;
     void* amp_user = nullptr;
@@ -131,8 +135,8 @@ struct DBuf {
     DBuf& operator=(DBuf&& o) noexcept {
         if (this != &o) {
             release();
-            ctx = o.ctx; p = o.p; n = o.n; cap = o.cap;
-            o.p = nullptr; o.n = 0; o.cap = 0;
+            ctx = o.ctx; p = o.p; n = o.n; cap = o.cap; from_big = o.from_big;
+            o.p = nullptr; o.n = 0; o.cap = 0; o.from_big = false;
         }
         return *this;
     }
@@ -144,6 +148,7 @@ struct DBuf {
     // Re-using a cached block right away is safe because all work of a context is on one stream.
     static constexpr size_t kBigBytes = size_t(64) << 20;
     size_t cap = 0;  // bytes actually held (big blocks may be slightly larger than requested)
+    bool from_big = false;   // block came from cudaMalloc / the context's big-block cache
     void alloc(jues_ctx* c, size_t n_) {
         release();
         ctx = c;
@@ -155,7 +160,8 @@ struct DBuf {
         const auto t0__ = std::chrono::steady_clock::now();
         cudaError_t e = cudaSuccess;
         cap = bytes;
-        if (bytes >= kBigBytes) {
+        from_big = bytes >= c->big_bytes;
+        if (from_big) {
             auto it = c->big_free.lower_bound(bytes);
             if (it != c->big_free.end() && it->first <= bytes + bytes / 8) {
                 p = it->second;
@@ -190,7 +196,7 @@ struct DBuf {
     }
     void release() {
         if (p) {
-            if (cap >= kBigBytes) {
+            if (from_big) {
                 ctx->big_free.emplace(cap, p);
                 ctx->big_cached_bytes += cap;
             } else {
@@ -200,6 +206,7 @@ struct DBuf {
             p = nullptr;
             n = 0;
             cap = 0;
+            from_big = false;
         }
     }
     void zero() { JUES_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream)); }

@@ -12,6 +12,10 @@
 
 namespace jues {
 
+static QuarterProbe g_probe = nullptr;
+static void* g_probe_user = nullptr;
+void set_quarter_probe(QuarterProbe fn, void* user) { g_probe = fn; g_probe_user = user; }
+
 const double* SynthGao::slab(jues_ctx* ctx, int64_t lo, int64_t cnt) {
     const int64_t plane = np * np * np;
     if ((int64_t)stage.n < plane * cnt) stage.alloc(ctx, (size_t)(plane * cnt));
@@ -207,6 +211,7 @@ void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4],
             TraceTimer tq(ctx, s == 0 ? "tei.q1" : s == 1 ? "tei.q2" : s == 2 ? "tei.q3" : "tei.q4");
             quarter(ctx, src, e, ax, Cm[ax], np, dp[ax], dst);
         }
+        if (g_probe) g_probe(g_probe_user, ctx, s, dst, nout);
         if (s < 3) src = dst;
         e[ax] = dp[ax];
     }

@@ -76,6 +76,10 @@ struct TransformWorkspace {
 void tei_transform_dev(jues_ctx* ctx, GaoSource& gao, const double* const Cm[4], const int64_t dp[4],
                        double* out, bool reference_order = false, TransformWorkspace* ws = nullptr);
 
+// testing hook: called after every quarter transform with (step 0..3, output pointer, elements)
+typedef void (*QuarterProbe)(void* user, jues_ctx* ctx, int step, const double* out, size_t n);
+void set_quarter_probe(QuarterProbe fn, void* user);
+
 // flops of the order tei_transform_dev would pick (for reporting)
 double tei_transform_flops(int64_t np, const int64_t dp[4], bool reference_order, bool streamed);
 

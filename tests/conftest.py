@@ -19,6 +19,9 @@ def pytest_configure(config):
 def ctx():
     """One library context on cuda:0 for the whole GPU test session."""
     import jues.jl_b200 as jb
-    c = jb.Context(0)
+    try:
+        c = jb.Context(0)
+    except jb.JuesError as e:            # library built, but no sm_100 device / driver on this machine
+        pytest.skip(f"no usable sm_100 device: {e}")
     yield c
     c.close()

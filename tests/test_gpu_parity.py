@@ -288,3 +288,33 @@ def test_virtual_synthetic_tensor_streams_like_the_dense_one(ctx):
     assert abs(e_v - orc.do_rccsd(wo)) <= E_TOL
     assert abs(m_v - orc.do_rmp2(wo)) <= E_TOL
     assert abs(d_v - orc.do_rccd(wo)) <= E_TOL
+
+
+# ---- determinism of the transform at the shape that exposed the round-1 release race ----------------
+def test_slab_transform_deterministic(ctx):
+    """Every quarter of the <vv|vv> slab transform (dims v,v,v,v/2) repeated inside one call must
+    reproduce the first run bit for bit (profiles/gemm_release_race_r02.md)."""
+    import ctypes as C
+    from jues.jl_b200 import _p, _f
+    nbf, nocc = 72, 10
+    v = nbf - nocc
+    Cao, Cav, eps = jb.synth.orbitals(nbf, nocc, 5)
+    g = jb.DeviceFourTensor.synth_eri(nbf, seed=5, scale=jb.synth.counter_scale(nbf), ctx=ctx)
+    reps = 4
+    try:
+        for r in range(2):
+            Cs = np.asfortranarray(Cav[:, r * (v // 2):(r + 1) * (v // 2)])
+            st = (C.c_double * (16 * reps))()
+            ctx._check(ctx._lib.jues_b200_transform_stress(ctx._h, g._h, _p(_f(Cav)), v, _p(_f(Cav)), v, _p(_f(Cav)), v,
+                                                           _p(Cs), v // 2, reps, st))
+            a = np.array(list(st)).reshape(reps, 4, 4)
+            assert a[:, :, 0].max() == 0.0, a[:, :, 0]
+    finally:
+        g.free()
+
+
+def test_gemm_repeatable(ctx):
+    for (tA, tB, M, N, K, b) in [("N", "N", 40000, 62, 144, 1), ("T", "N", 124, 30000, 144, 1),
+                                 ("N", "N", 124, 124, 144, 300), ("T", "N", 700, 700, 700, 1)]:
+        nb, w = ctx.gemm_stress(tA, tB, M, N, K, b, reps=5)
+        assert nb == 0 and w == 0.0, (tA, tB, M, N, K, b, nb, w)
