@@ -31,16 +31,22 @@ struct HostGaoHolder {
     std::unique_ptr<GaoSource> src;
 };
 
-void make_host_gao(jues_ctx* ctx, HostGaoHolder& h, const double* gao, int64_t nao, bool need_resident) {
+// stream == true: the consumer is the sharded one-pass transform, which reads each AO block exactly once
+// (RMP2, RCCD, RCCSD, mRCCD): blocks are uploaded straight from the caller's array, 1/P of it per rank.
+// stream == false: the AO tensor is read several times (tei_transform in arbitrary contraction order,
+// get_fock + coupled cluster): keep a device copy when it fits comfortably.
+void make_host_gao(jues_ctx* ctx, HostGaoHolder& h, const double* gao, int64_t nao, bool stream) {
     JUES_REQUIRE(gao != nullptr && nao > 0, "null or empty gao");
     const int64_t np = round_up(nao, 2);
     const double bytes = (double)np * np * np * np * 8.0;
-    flush_big_cache(ctx);
-    const double avail = (double)free_device_bytes() + 0.0;
     const bool force_stream = getenv("JUES_B200_FORCE_STREAM") != nullptr;  // testing hook
-    // coupled cluster keeps a second, re-ordered copy next to the AO tensor: budget twice the bytes
-    const double need = need_resident ? 2.0 * bytes : bytes;
-    if (!force_stream && need < 0.45 * avail) {
+    if (stream || force_stream) {
+        h.src.reset(new HostGao(gao, nao, np));
+        return;
+    }
+    flush_big_cache(ctx);                       // make room for the resident copy
+    const double avail = (double)free_device_bytes() + 0.0;
+    if (bytes < 0.45 * avail) {
         Timer t(ctx, "h2d.gao");
         h.dense.alloc(ctx, (size_t)(np * np * np * np));
         upload_padded_gao(ctx, h.dense.p, gao, nao, np);
@@ -260,7 +266,7 @@ extern "C" int jues_b200_rmp2(jues_ctx* ctx, const double* gao, int64_t nao, con
     Problem P;
     setup_problem(ctx, P, nao, Cao, nocc, Cav, nvir, eps);
     HostGaoHolder h;
-    make_host_gao(ctx, h, gao, nao, false);
+    make_host_gao(ctx, h, gao, nao, true);
     *e_mp2 = rmp2_dev(ctx, P, *h.src);
     JUES_API_END(ctx)
 }
@@ -602,7 +608,7 @@ extern "C" int jues_b200_auto_rccsd(jues_ctx* ctx, const double* gao, int64_t na
     begin_call(ctx);
     Timer total(ctx, "total");
     HostGaoHolder h;
-    make_host_gao(ctx, h, gao, nao, true);
+    make_host_gao(ctx, h, gao, nao, false);
     run_auto(ctx, *h.src, hao, Ca, nmo, ndocc, opt, e_cc, e_pt, iterations, converged, e_hist, rms_hist,
              T1_out, T2_out);
     JUES_API_END(ctx)

@@ -51,45 +51,18 @@ double rmp2_dev(jues_ctx* ctx, Problem& P, GaoSource& gao) {
     int64_t b0, vs;
     slab_of(ctx, v, &b0, &vs);   // this rank's slab of the virtual index b (everything when nranks == 1)
     // E = sum_{ij a b} v_ijab (2 v_ijab - v_ijba) / D with v_ijba = v_jiab: every (a, b in slab) block is
-    // self-contained, so the energy needs no exchange but the final scalar.
-    DTen ijab;
-    if (gao.resident()) {
-        // resident AO tensor: transform only this rank's slab, (ia|j b_S)
-        DTen t4(ctx, o, v, o, vs);
-        {
-            Timer t(ctx, "mp2.transform");
-            const double* Cm[4] = {P.Co.p, P.Cv.p, P.Co.p, P.Cv.p + b0 * gao.np};
-            const int64_t dp[4] = {o, v, o, vs};
-            tei_transform_dev(ctx, gao, Cm, dp, t4.p());
-        }
-        Timer t(ctx, "mp2.energy");
-        ijab.alloc(ctx, o, o, v, vs);
-        permute_axpby(ctx, 1.0, t4, "iajb", 0.0, ijab, "ijab");   // <ij|ab> (IntegralTransformation.jl:96-98)
-        return all_reduce_scalar(ctx, mp2_energy(ctx, ijab.p(), P.eo.p, P.ev.p, o, v, b0, vs));
-    }
-    // streamed AO tensor: contracted over sigma first with the occupied index in the last slot
-    // ((ia|jb) = (ia|bj): an N^3 x o accumulator instead of N^3 x v).  The transform is linear in
-    // gao, so each rank streams only its share of the sigma range -- generation and the dominant
-    // first quarter are divided by the number of ranks -- and the partial (ia|bj) tensors are summed.
-    DTen t4(ctx, o, v, v, o);
+    // self-contained, so the energy needs no exchange but the final scalar.  <ij|a b_S> = (ia|j b_S)
+    // (IntegralTransformation.jl:96-98) comes out of the sharded one-pass transform already in the layout
+    // the energy kernel reads: each rank touches 1/P of the AO tensor, occupied indices are contracted
+    // first (2 N^4 o / P flops), and the exchanged block is only o^2 (N/P) v.
+    DBuf ijab;
     {
         Timer t(ctx, "mp2.transform");
-        if (ctx->nranks > 1) {
-            const int64_t per = round_up((gao.np + ctx->nranks - 1) / ctx->nranks, 2);
-            gao.sig_lo = std::min<int64_t>(gao.np, per * ctx->rank);
-            gao.sig_hi = std::min<int64_t>(gao.np, per * (ctx->rank + 1));
-        }
-        const double* Cm[4] = {P.Co.p, P.Cv.p, P.Cv.p, P.Co.p};
-        const int64_t dp[4] = {o, v, v, o};
-        tei_transform_dev(ctx, gao, Cm, dp, t4.p());
-        gao.sig_lo = 0; gao.sig_hi = -1;
-        all_reduce_sum(ctx, t4.p(), (size_t)t4.t.size());
+        const std::vector<int64_t> counts((size_t)ctx->nranks, vs);
+        tei_transform_sharded(ctx, gao, P.Co.p, o, P.Co.p, o, P.Cv.p, v, P.Cv.p, counts, ijab);
     }
     Timer t(ctx, "mp2.energy");
-    ijab.alloc(ctx, o, o, v, v);
-    permute_axpby(ctx, 1.0, t4, "iabj", 0.0, ijab, "ijab");
-    const double e = mp2_energy(ctx, ijab.p() + b0 * o * o * v, P.eo.p, P.ev.p, o, v, b0, vs);
-    return all_reduce_scalar(ctx, e);
+    return all_reduce_scalar(ctx, mp2_energy(ctx, ijab.p, P.eo.p, P.ev.p, o, v, b0, vs));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -177,95 +150,67 @@ struct CC {
     bool fock = false;
     // amplitudes (replicated)
     DTen T1, T2, T1n, T2n;
-    TransformWorkspace tws;   // shared by the class transforms, released before the sweeps
     PermCache pcache;         // permuted operand copies (static: once; amplitude-derived: once per sweep)
 
     CC(jues_ctx* c, Problem& p, bool s) : ctx(c), P(p), singles(s), o(p.o), v(p.v) { slab_of(c, v, &b0, &vs); }
 
-    void klass(GaoSource& gphys, DTen& out, const char* slots, bool slab4) {
-        const double* Cm[4];
-        int64_t dp[4];
-        for (int q = 0; q < 4; ++q) {
-            Cm[q] = slots[q] == 'o' ? P.Co.p : P.Cv.p;
-            dp[q] = slots[q] == 'o' ? o : v;
-        }
-        if (slab4) {
-            Cm[3] = P.Cv.p + b0 * gphys.np;   // columns [b0, b0+vs) of Cav
-            dp[3] = vs;
-        }
-        out.alloc(ctx, dp[0], dp[1], dp[2], dp[3]);
-        if (gphys.resident()) {
-            tei_transform_dev(ctx, gphys, Cm, dp, out.p(), false, &tws);
-            return;
-        }
-        // A streamed AO tensor must be contracted over its last index first, and the first quarter's
-        // output is N^3 x d4: use <pq|rs> = <rq|ps> = <ps|rq> = <qp|sr> (8 slot orders in all) to put
-        // the SMALLEST extent in the last slot, transform, and permute back.
-        static const int sym[8][4] = {{0, 1, 2, 3}, {0, 3, 2, 1}, {1, 0, 3, 2}, {1, 2, 3, 0},
-                                      {2, 1, 0, 3}, {2, 3, 0, 1}, {3, 0, 1, 2}, {3, 2, 1, 0}};
-        int best = 0;
-        for (int g = 1; g < 8; ++g)
-            if (dp[sym[g][3]] < dp[sym[best][3]]) best = g;
-        if (best == 0) {
-            tei_transform_dev(ctx, gphys, Cm, dp, out.p(), false, &tws);
-            return;
-        }
-        const double* Cm2[4];
-        int64_t dp2[4];
-        char ly[5] = {0, 0, 0, 0, 0};
-        const char lx[5] = "pqrs";
-        for (int k = 0; k < 4; ++k) { Cm2[k] = Cm[sym[best][k]]; dp2[k] = dp[sym[best][k]]; ly[k] = lx[sym[best][k]]; }
-        DTen y(ctx, dp2[0], dp2[1], dp2[2], dp2[3]);
-        tei_transform_dev(ctx, gphys, Cm2, dp2, y.p(), false, &tws);
-        permute_axpby(ctx, 1.0, y, ly, 0.0, out, lx);
-    }
-
-    // A class every rank needs in full: with a streamed AO tensor each rank transforms only its
-    // share of the sigma planes (the transform is linear) and the partial tensors are summed.
-    void replicated_klass(GaoSource& gphys, DTen& out, const char* slots) {
-        const bool split = !gphys.resident() && ctx->nranks > 1;
-        if (split) {
-            const int64_t per = round_up((gphys.np + ctx->nranks - 1) / ctx->nranks, 2);
-            gphys.sig_lo = std::min<int64_t>(gphys.np, per * ctx->rank);
-            gphys.sig_hi = std::min<int64_t>(gphys.np, per * (ctx->rank + 1));
-        }
-        klass(gphys, out, slots, false);
-        if (split) {
-            gphys.sig_lo = 0; gphys.sig_hi = -1;
-            all_reduce_sum(ctx, out.p(), (size_t)out.t.size());
-        }
-    }
-
-    void all_classes(GaoSource& gphys) {
-        replicated_klass(gphys, V, "oovv");
-        replicated_klass(gphys, J, "ovov");
-        replicated_klass(gphys, oooo, "oooo");
-        klass(gphys, W4, "vvvv", true);
-        if (singles) {
-            replicated_klass(gphys, ooov, "ooov");
-            klass(gphys, OA, "vvov", true);
-            klass(gphys, OB, "vovv", true);
-        }
+    // All integral classes from ONE pass over the AO tensor, shared by the ranks (tei_transform_sharded):
+    // the slab M[p,q,r,s] = <pq|rs> over all MO p, q, r and this rank's columns s = [its share of the
+    // occupied orbitals | its virtual slab]; the classes are sub-blocks of it (RCCSD.jl:117-132 runs 15
+    // separate transforms, mRCCSD.jl:102-110 shows 6 classes suffice).  The o^2 v^2-sized classes every rank
+    // needs in full are all-gathered from their slabs.
+    void extract(const DBuf& M, int64_t nmo, int64_t nsl, int64_t p0, int64_t q0, int64_t r0, int64_t s0,
+                 double* dst, int64_t e0, int64_t e1, int64_t e2, int64_t e3) {
+        const int64_t sd[4] = {nmo, nmo, nmo, nsl}, dd[4] = {e0, e1, e2, e3};
+        block_copy(ctx, M.p + p0 + nmo * (q0 + nmo * (r0 + nmo * s0)), sd, dst, dd, dd);
     }
 
     void build_integrals(GaoSource& gao) {
         {
             Timer t(ctx, "cc.transform");
-            // transforming g'[mu,lam,nu,sig] = g[mu,nu,lam,sig] slot by slot yields <pq|rs> directly
-            if (gao.resident()) {
-                const int64_t np = gao.np;
-                DTen gp(ctx, np, np, np, np);
-                Ten g(const_cast<double*>(gao.base()), np, np, np, np);
-                permute_axpby(ctx, 1.0, g, "mnls", 0.0, gp, "mlns");
-                DeviceGao gphys(gp.p(), gao.n, np);
-                all_classes(gphys);
-            } else {
-                gao.phys = true;     // slabs are produced in [mu,lam,nu,sig] order
-                all_classes(gao);
-                gao.phys = false;
+            const int P_ = ctx->nranks;
+            const int64_t np = gao.np, nmo = o + v;
+            const int64_t oP = round_up(o, P_), os = oP / P_, nsl = os + vs;
+            DBuf Call(ctx, (size_t)(np * nmo)), Cs(ctx, (size_t)(np * nsl * P_));
+            JUES_CUDA(cudaMemcpyAsync(Call.p, P.Co.p, (size_t)(np * o) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            JUES_CUDA(cudaMemcpyAsync(Call.p + np * o, P.Cv.p, (size_t)(np * v) * 8, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+            Cs.zero();
+            for (int d = 0; d < P_; ++d) {
+                const int64_t i0 = std::min<int64_t>(o, d * os), i1 = std::min<int64_t>(o, (d + 1) * os);
+                if (i1 > i0)
+                    JUES_CUDA(cudaMemcpyAsync(Cs.p + np * nsl * d, P.Co.p + np * i0, (size_t)(np * (i1 - i0)) * 8,
+                                              cudaMemcpyDeviceToDevice, ctx->stream));
+                JUES_CUDA(cudaMemcpyAsync(Cs.p + np * (nsl * d + os), P.Cv.p + np * vs * d, (size_t)(np * vs) * 8,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            DBuf M;
+            tei_transform_sharded(ctx, gao, Call.p, nmo, Call.p, nmo, Call.p, nmo, Cs.p,
+                                  std::vector<int64_t>((size_t)P_, nsl), M);
+            TraceTimer tc(ctx, "cc.classes");
+            // slabs of the replicated classes, gathered in place
+            V.alloc(ctx, o, o, v, v);
+            extract(M, nmo, nsl, 0, 0, o, os, V.p() + b0 * o * o * v, o, o, v, vs);          // <ij|ab>
+            all_gather_inplace(ctx, V.p(), (size_t)(o * o * v * vs));
+            J.alloc(ctx, o, v, o, v);
+            extract(M, nmo, nsl, 0, o, 0, os, J.p() + b0 * o * v * o, o, v, o, vs);          // <mb|je>
+            all_gather_inplace(ctx, J.p(), (size_t)(o * v * o * vs));
+            oooo.alloc(ctx, o, o, o, oP);                                                      // <mn|ij>, j shared out
+            extract(M, nmo, nsl, 0, 0, 0, 0, oooo.p() + (int64_t)ctx->rank * os * o * o * o, o, o, o, os);
+            all_gather_inplace(ctx, oooo.p(), (size_t)(o * o * o * os));
+            oooo.t.d[3] = o;                                                                   // the padding shares are zero
+            W4.alloc(ctx, v, v, v, vs);
+            extract(M, nmo, nsl, o, o, o, os, W4.p(), v, v, v, vs);                            // <ef|ab>
+            if (singles) {
+                ooov.alloc(ctx, o, o, o, v);
+                extract(M, nmo, nsl, 0, 0, 0, os, ooov.p() + b0 * o * o * o, o, o, o, vs);   // <mn|ie>
+                all_gather_inplace(ctx, ooov.p(), (size_t)(o * o * o * vs));
+                OA.alloc(ctx, v, v, o, vs);
+                extract(M, nmo, nsl, o, o, 0, os, OA.p(), v, v, o, vs);                        // <ef|mb>
+                OB.alloc(ctx, v, o, v, vs);
+                extract(M, nmo, nsl, o, 0, o, os, OB.p(), v, o, v, vs);                        // <aj|eb>
             }
         }
-        tws.buf[0].release(); tws.buf[1].release();
         Timer t(ctx, "cc.static");
         if (getenv("JUES_B200_PLAIN_LADDER") == nullptr) {
             sa_ld = round_up(sa_pairs(v), 2);

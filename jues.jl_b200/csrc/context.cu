@@ -44,6 +44,7 @@ extern "C" int jues_b200_init(jues_ctx** out, int device) {
         if (const char* mb = getenv("JUES_B200_BIG_MB")) ctx->big_bytes = (size_t)std::max(1, atoi(mb)) << 20;
         ctx->sync_comm = getenv("JUES_B200_SYNC_COMM") != nullptr;
         JUES_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        JUES_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
         {   // keep freed blocks in the stream-ordered pool (all work of a context is on one stream)
             cudaMemPool_t pool;
             JUES_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -81,6 +82,7 @@ extern "C" void jues_b200_finalize(jues_ctx* ctx) {
     ctx->big_free.clear();
     if (ctx->red_dev) cudaFree(ctx->red_dev);
     if (ctx->red_host) cudaFreeHost(ctx->red_host);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

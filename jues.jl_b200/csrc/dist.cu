@@ -20,6 +20,10 @@ struct NcclApi {
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -47,6 +51,10 @@ void load_nccl() {
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
     g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+    g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
+    g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
     g_nccl.handle = h;
 }
@@ -87,6 +95,33 @@ void all_reduce_sum(jues_ctx* ctx, double* buf, size_t count) {
     ctx->stats.collective_bytes += (double)count * 8.0;
 }
 
+void all_to_all_v(jues_ctx* ctx, const double* send, const size_t* send_off, const size_t* send_cnt,
+                  double* recv, const size_t* recv_off, const size_t* recv_cnt) {
+    const int me = ctx->rank;
+    // own block: plain device copy
+    if (send_cnt[me])
+        JUES_CUDA(cudaMemcpyAsync(recv + recv_off[me], send + send_off[me], send_cnt[me] * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->nranks == 1) return;
+    if (ctx->sync_comm) JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
+    double got = 0.0;
+    for (int k = 1; k < ctx->nranks; ++k) {
+        const int to = (me + k) % ctx->nranks, from = (me - k + ctx->nranks) % ctx->nranks;
+        if (send_cnt[to])
+            nccl_check(g_nccl.Send(send + send_off[to], send_cnt[to], ncclDouble, to, (ncclComm_t)ctx->nccl_comm,
+                                   ctx->stream), "ncclSend");
+        if (recv_cnt[from])
+            nccl_check(g_nccl.Recv(recv + recv_off[from], recv_cnt[from], ncclDouble, from,
+                                   (ncclComm_t)ctx->nccl_comm, ctx->stream), "ncclRecv");
+        got += (double)recv_cnt[from] * 8.0;
+    }
+    nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
+    if (ctx->sync_comm) JUES_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.collectives++;
+    ctx->stats.collective_bytes += got;
+}
+
 double all_reduce_scalar(jues_ctx* ctx, double x) {
     if (ctx->nranks == 1) return x;
     double* slot = ctx->red_dev + ctx->red_cap - 2;
@@ -121,8 +156,8 @@ extern "C" int jues_b200_init_dist(jues_ctx* ctx, int rank, int nranks, const un
     JUES_API_BEGIN(ctx)
     JUES_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
     dist_teardown(ctx);
-    ctx->rank = rank;
-    ctx->nranks = nranks;
+    ctx->rank = 0;
+    ctx->nranks = 1;
     if (nranks > 1) {
         JUES_REQUIRE(id != nullptr, "null NCCL unique id");
         load_nccl();
@@ -130,12 +165,21 @@ extern "C" int jues_b200_init_dist(jues_ctx* ctx, int rank, int nranks, const un
         memcpy(&uid, id, 128);
         ncclComm_t comm;
         nccl_check(g_nccl.CommInitRank(&comm, nranks, uid, rank), "ncclCommInitRank");
+        // rank / nranks are published only once the communicator exists (a failed init leaves a
+        // consistent single-rank context behind)
         ctx->nccl_comm = comm;
+        ctx->rank = rank;
+        ctx->nranks = nranks;
         // first collective sets up the NVLink connections (seconds): do it here, not inside a timed call
         double* slot = ctx->red_dev + ctx->red_cap - 2;
         JUES_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), ctx->stream));
         all_reduce_sum(ctx, slot, 1);
         all_gather_inplace(ctx, ctx->red_dev, 1);
+        {   // ... and the point-to-point connections of the transform's exchange
+            std::vector<size_t> off((size_t)nranks), cnt((size_t)nranks, 1);
+            for (int d = 0; d < nranks; ++d) off[d] = (size_t)d;
+            all_to_all_v(ctx, ctx->red_dev, off.data(), cnt.data(), ctx->red_dev + nranks, off.data(), cnt.data());
+        }
         JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     JUES_API_END(ctx)

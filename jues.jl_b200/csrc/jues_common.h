@@ -74,6 +74,7 @@ struct jues_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;   // second stream: exchanges / copies that overlap compute
     jues::PFN_encodeTiled encode = nullptr;
     std::string last_error;
     jues::Stats stats;
@@ -258,6 +259,15 @@ inline void resolve_timers(jues_ctx* ctx) {
     }
     ctx->pending.clear();
 }
+
+// Run a section on another stream: every helper launches on ctx->stream, so the scope swaps it.
+// No stream-ordered allocation may happen inside (DBuf frees are ordered on the stream they see).
+struct StreamScope {
+    jues_ctx* ctx;
+    cudaStream_t saved;
+    StreamScope(jues_ctx* c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
+    ~StreamScope() { ctx->stream = saved; }
+};
 
 // JUES_B200_TRACE=1: fine-grained CUDA-event timings
 struct TraceTimer {

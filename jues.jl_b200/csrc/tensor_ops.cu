@@ -422,33 +422,38 @@ __global__ void diis_combine_kernel(DiisVecs d, long long n, double* __restrict_
     }
 }
 
+// Element (mu, a1, a2, a3) of the block; one warp per row (a1, a2, a3) so that the pair index of the
+// (lam, sig) / (nu, .) part and all divisions are done once per row, not per element.
 __global__ void synth_eri_kernel(double* __restrict__ g, long long n, long long np, long long lam_lo,
                                  long long lam_count, long long sig_lo, long long sig_count,
                                  unsigned long long seed, double scale, int phys) {
-    const long long total = np * np * lam_count * sig_count;
-    long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; L < total; L += stride) {
-        long long r = L;
-        const unsigned long long mu = r % np; r /= np;
-        unsigned long long nu = r % np; r /= np;
+    const long long rows = np * lam_count * sig_count;
+    const int lane = threadIdx.x & 31;
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long rstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (; row < rows; row += rstride) {
+        long long r = row;
+        unsigned long long nu = (unsigned long long)(r % np); r /= np;
         unsigned long long lam = (unsigned long long)(r % lam_count) + lam_lo;
         if (phys) { const unsigned long long tmp = nu; nu = lam; lam = tmp; }  // g'[mu,lam,nu,sig]
         const unsigned long long sig = (unsigned long long)(r / lam_count) + sig_lo;
-        double val = 0.0;
-        if (mu < (unsigned long long)n && nu < (unsigned long long)n && lam < (unsigned long long)n &&
-            sig < (unsigned long long)n) {
-            unsigned long long hi = mu > nu ? mu : nu, lo = mu > nu ? nu : mu;
-            const unsigned long long P = hi * (hi + 1) / 2 + lo;
-            hi = lam > sig ? lam : sig; lo = lam > sig ? sig : lam;
-            const unsigned long long Q = hi * (hi + 1) / 2 + lo;
-            hi = P > Q ? P : Q; lo = P > Q ? Q : P;
-            const unsigned long long K = hi * (hi + 1) / 2 + lo;
-            const unsigned long long h = splitmix64(seed ^ K);
-            const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
-            val = scale * (2.0 * u - 1.0);
+        double* __restrict__ dst = g + row * np;
+        const bool live = nu < (unsigned long long)n && lam < (unsigned long long)n && sig < (unsigned long long)n;
+        const unsigned long long hi2 = lam > sig ? lam : sig, lo2 = lam > sig ? sig : lam;
+        const unsigned long long Q = hi2 * (hi2 + 1) / 2 + lo2;
+        for (unsigned long long mu = lane; mu < (unsigned long long)np; mu += 32) {
+            double val = 0.0;
+            if (live && mu < (unsigned long long)n) {
+                const unsigned long long hi = mu > nu ? mu : nu, lo = mu > nu ? nu : mu;
+                const unsigned long long P = hi * (hi + 1) / 2 + lo;
+                const unsigned long long h2 = P > Q ? P : Q, l2 = P > Q ? Q : P;
+                const unsigned long long K = h2 * (h2 + 1) / 2 + l2;
+                const unsigned long long h = splitmix64(seed ^ K);
+                const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+                val = scale * (2.0 * u - 1.0);
+            }
+            dst[mu] = val;
         }
-        g[L] = val;
     }
 }
 
@@ -507,11 +512,19 @@ void lincomb2(jues_ctx* ctx, size_t n, double a, const double* x1, double b, con
 
 void permute_axpby(jues_ctx* ctx, double alpha, const Ten& in, const char* ii, double beta,
                    const Ten& out, const char* io) {
+    int64_t st[4] = {1, 1, 1, 1};
+    int64_t s = 1;
+    for (int q = 0; q < in.rank; ++q) { st[q] = s; s *= in.d[q]; }
+    permute_axpby_strided(ctx, alpha, in, st, ii, beta, out, io);
+}
+
+void permute_axpby_strided(jues_ctx* ctx, double alpha, const Ten& in, const int64_t in_strides[4],
+                           const char* ii, double beta, const Ten& out, const char* io) {
     const int rank = (int)strlen(ii);
     JUES_REQUIRE(rank == (int)strlen(io) && rank == in.rank && rank == out.rank && rank >= 1 && rank <= 4,
                  "permute: rank mismatch");
-    long long sin_in[4], s = 1;
-    for (int q = 0; q < rank; ++q) { sin_in[q] = s; s *= in.d[q]; }
+    long long sin_in[4];
+    for (int q = 0; q < rank; ++q) sin_in[q] = in_strides[q];
     long long n[4] = {1, 1, 1, 1}, sin[4] = {0, 0, 0, 0}, sout[4] = {0, 0, 0, 0};
     long long so = 1;
     for (int q = 0; q < rank; ++q) {
@@ -748,8 +761,12 @@ void synth_eri_block(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padd
                      bool phys) {
     const size_t total = (size_t)n_padded * n_padded * lam_cnt * sig_cnt;
     if (!total) return;
-    synth_eri_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(g, n_logical, n_padded, lam_lo, lam_cnt,
-                                                                        sig_lo, sig_cnt, seed, scale, phys ? 1 : 0);
+    long long blocks = (long long)((total / (size_t)n_padded + 7) / 8);    // 8 rows (warps) per block
+    const long long capb = (long long)ctx->sm_count * 32;
+    if (blocks > capb) blocks = capb;
+    if (blocks < 1) blocks = 1;
+    synth_eri_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(g, n_logical, n_padded, lam_lo, lam_cnt,
+                                                                sig_lo, sig_cnt, seed, scale, phys ? 1 : 0);
     AUX_LAUNCHED(ctx);
 }
 

@@ -47,6 +47,11 @@ int ew_grid(jues_ctx* ctx, size_t n, int threads);
 void permute_axpby(jues_ctx* ctx, double alpha, const Ten& in, const char* ii, double beta,
                    const Ten& out, const char* io);
 
+// the same with an input VIEW: in.d are the extents of the view, in_strides its element strides (a block of
+// a larger dense tensor); the output is dense
+void permute_axpby_strided(jues_ctx* ctx, double alpha, const Ten& in, const int64_t in_strides[4],
+                           const char* ii, double beta, const Ten& out, const char* io);
+
 // y = a*x + b*y  (same layout, n elements)
 void axpby(jues_ctx* ctx, size_t n, double a, const double* x, double b, double* y);
 // y = a*x1 + b*x2

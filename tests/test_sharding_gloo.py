@@ -205,3 +205,96 @@ def test_auto_rccsd_and_triples_over_gloo():
         assert p.exitcode == 0
     err, dpt, mag = q.get(timeout=5)
     assert err < 1e-13 and dpt < 1e-14 and mag > 1e-8
+
+
+# ---- the sharded one-pass integral transformation (tests/transform_model.py == csrc/transform.cu) ---------
+import transform_model as tm
+
+
+def _classes_reference(g, Cao, Cavp, b0, b1):
+    I6 = fm.unique_integrals(g, Cao, Cavp)
+    R = sm.rank_integrals(I6, b0, b1)
+    return R
+
+
+@pytest.mark.parametrize("singles", [True, False])
+def test_transform_model_single_rank(singles):
+    N, o = 9, 3
+    g, Cao, Cav, eps = _setup(N, o, 3)
+    R = tm.cc_classes(g, Cao, Cav, tm.SoloComm(), singles=singles)
+    ref = _classes_reference(g, Cao, Cav, 0, N - o)
+    for k in R:
+        assert np.abs(R[k] - ref[k]).max() < 1e-13, k
+    w = orc.Wfn(o, N - o, eps, Cao, Cav, g)
+    ijab = tm.mp2_slab(g, Cao, Cav, tm.SoloComm())
+    assert np.abs(ijab - orc.get_eri(w, "OOVV")).max() < 1e-13
+
+
+def _transform_worker(rank, world, port, N, o, seed, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class Comm:
+            size = world
+
+            def alltoall(self, parts):
+                shapes = [list(p.shape) for p in parts]
+                # nu-block extents differ per source: exchange shapes first
+                mine = torch.tensor([s[2] for s in shapes[rank:rank + 1]], dtype=torch.int64)
+                allnb = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+                dist.all_gather(allnb, mine)
+                out = []
+                reqs = []
+                for d in range(world):
+                    shp = list(parts[rank].shape)
+                    shp[2] = int(allnb[d][0])
+                    out.append(torch.empty(shp, dtype=torch.float64))
+                for d in range(world):
+                    if d == rank:
+                        out[d].copy_(torch.from_numpy(parts[d]))
+                    else:
+                        reqs.append(dist.isend(torch.from_numpy(parts[d]), d))
+                        reqs.append(dist.irecv(out[d], d))
+                for r_ in reqs:
+                    r_.wait()
+                return [x.numpy() for x in out]
+
+            def allgather_last(self, x):
+                xs = np.ascontiguousarray(np.moveaxis(x, -1, 0))
+                parts = [torch.empty(xs.shape, dtype=torch.float64) for _ in range(world)]
+                dist.all_gather(parts, torch.from_numpy(xs))
+                return np.moveaxis(np.concatenate([p.numpy() for p in parts], axis=0), 0, -1)
+        Comm.rank = rank
+        g, Cao, Cav, eps = _setup(N, o, seed)
+        v = N - o
+        vp, b0, b1 = sm.slab_bounds(v, world, rank)
+        Cavp = np.pad(Cav, ((0, 0), (0, vp - v)))
+        R = tm.cc_classes(g, Cao, Cavp, Comm(), singles=True)
+        ref = _classes_reference(g, Cao, Cavp, b0, b1)
+        err = max(float(np.abs(R[k] - ref[k]).max()) for k in R)
+        ijab = tm.mp2_slab(g, Cao, Cavp, Comm())
+        w = orc.Wfn(o, v, eps, Cao, Cav, g)
+        full = np.pad(orc.get_eri(w, "OOVV"), ((0, 0), (0, 0), (0, vp - v), (0, vp - v)))
+        err = max(err, float(np.abs(ijab - full[:, :, :, b0:b1]).max()))
+        q.put(err)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_transform_over_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_transform_worker, args=(r, world, port, 10, 3, 21, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    for _ in range(world):
+        assert q.get(timeout=5) < 1e-13
