@@ -6,38 +6,54 @@ CPU".  One JSON line is printed by rank 0:
 
   * a "step" is ONE RCCSD sweep (all intermediates, T1 and T2 updates, and the energy the reference
     evaluates every sweep -- RCCSD.jl:150-173,104) on device-resident integrals and amplitudes;
-    `ms_per_step` is therefore the "RCCSD s/iteration" figure (x1000) and `value` the same thing
-    as whole-job FP64 throughput: floating-point operations the GEMM kernels executed per sweep
-    (never more than the algorithmic count F_alg of SURVEY.md section 8a) / seconds per sweep.
-  * `tei_transform` holds the 4-index transform part of the metric (TFLOP/s of the full
-    tei_transform(gao, C) of the same AO tensor, executed flops = 8 N^5).
-  * `e2e` is the same metric through the reference-facing C-ABI call with HOST buffers (pinned):
-    one complete do_rccsd (H2D of gao/C/eps + integral transformation + 40 sweeps + energy D2H).
+    `ms_per_step` is the "RCCSD s/iteration" figure (x1000) and `value` the same thing as whole-job
+    FP64 throughput: floating-point operations the GEMM kernels of all ranks EXECUTED per sweep
+    (counted by the library per launch) / seconds per sweep.  The algorithm executes fewer flops than
+    SURVEY.md section 8a's F_alg and far fewer than the reference's literal F_ref; throughput normalised
+    by those counts is reported as labelled extras (`config.alg_normalised_tflops`, `.ref_normalised_tflops`),
+    never as `value`.
+  * `tei_transform` holds the 4-index transform part of the metric: the sharded one-pass transform that
+    produces every integral class of the run (executed flops, ms, fraction of the FP64 peak) and, on one
+    GPU, the full tei_transform(gao, C).
+  * `e2e` is the same metric through the reference-facing C-ABI call with HOST buffers (pinned): one
+    complete do_rccsd (H2D of this rank's share of gao + integral transformation + 40 sweeps + D2H).
   * `roofline` is the dominant kernel (the TMA+DMMA FP64 GEMM at the shape with the largest share of
-    the sweep: the ring products (ov x ov)(ov x ov) on one GPU, the particle-particle-ladder slab on
-    several), timed live with CUDA events on the library's stream, against the measured cuBLAS FP64
-    peak of this pool (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json records no FP64 figure).
-  * `cpu_baseline` is the oracle (numpy restatement of the reference's literal algorithm, "port")
-    timed on this box's host cores on a bounded sample.
-  * `next_rows` (extra, N=1 only): AutoRCCSD.do_rccsd with the (T) correction on the same inputs through
-    the C ABI from host buffers -- sweeps to convergence, Fock build and (T) times.
+    the sweep), its launch duration measured IN the sweep (one CUDA-event pair per launch on the library's
+    stream, `jues_b200_set_trace(ctx, 2)`), the isolated back-to-back figure beside it, against the measured
+    cuBLAS FP64 peak of this pool (profiles/fp64_peak_r01.json; MEASURED_PEAKS.json has no FP64 figure).
+  * `parity`: the per-sweep energies of the timed run against the committed oracle trace for this shape
+    (tests/golden/bench_ehist_nbf*_nocc20.npz, made by tests/golden/make_bench_golden.py from the literal
+    reference algorithm); the process exits non-zero when |dE| exceeds 1e-10 Eh.
+  * `cpu_baseline` is the oracle (numpy restatement of the reference's literal algorithm, "port") timed on
+    this box's host cores on a bounded sample.
+  * `large`: the configurations the metric's targets are quoted on -- RCCSD nbf=300/nocc=60 (fits one GPU:
+    strong scaling over N) and, at N=8, BASELINE config 5 (nbf=460/nocc=60): s/iteration, executed TFLOP/s
+    per GPU, transform time and TFLOP/s, communication ms per sweep.
+  * `next_rows` (extra, N=1 only): AutoRCCSD.do_rccsd with the (T) correction on the same inputs.
 
-`--impl reference` times the reference's CPU algorithm (the oracle port; there is no Julia here)
-on the same config and prints the same line shape.
+`--impl reference` times the reference's CPU algorithm (the oracle port; there is no Julia here) on the
+same shapes, with every host core, on a bounded sample, and prints the same line shape.
 
-Workload at N=1: BASELINE config 3 (RCCSD, synthetic ERIs, nbf=120, nocc=20), the largest
-single-GPU configuration in BASELINE.json (the nbf=460 configuration the metric is quoted on
-needs 205 GB for <vv|vv> alone and is the 8-GPU case).
+Workload at N=1: BASELINE config 3 (RCCSD, synthetic ERIs, nbf=120, nocc=20), the largest of BASELINE's
+named single-GPU configurations; at N>1 it grows with N at fixed nocc (weak scaling).
 """
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # The reference arm uses every host core: torch.distributed.run exports OMP_NUM_THREADS=1 for N>1,
+    # and OpenBLAS reads its thread count when numpy is imported -- so this comes first.
+    _cores = str(os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = _cores
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -48,32 +64,28 @@ NBF, NOCC = 120, 20
 WEAK_NVIR = {1: 100, 2: 124, 4: 152, 8: 192}   # F_alg(nocc=20, nvir) ~ N * F_alg(20, 100)
 SEED = 2024
 REF_MAXIT = 40          # RCCSD.jl:36
+E_TOL = 1e-10           # north_star: correlation energies within 1e-10 Eh
+LARGE = {"strong": (300, 60), "c5": (460, 60)}
 
 
-def flops_alg_rccsd(o, v):
-    """F_alg of SURVEY.md section 8a (factorised RCCSD sweep): jues.jl_b200/flops.py."""
+def _flops():
     from importlib import import_module
-    return import_module("jues.jl_b200.flops").rccsd_iter_alg(o, v)
+    return import_module("jues.jl_b200.flops")
 
 
-def flops_ref_rccsd(o, v):
-    """F_ref: the reference's literal sweep (Wabef built and applied, 13 ring-type terms)."""
-    from importlib import import_module
-    return import_module("jues.jl_b200.flops").rccsd_iter_ref(o, v)
+def golden_trace(nbf, nocc):
+    p = os.path.join(ROOT, "tests", "golden", f"bench_ehist_nbf{nbf}_nocc{nocc}.npz")
+    if not os.path.exists(p):
+        return None, os.path.relpath(p, ROOT)
+    return np.load(p), os.path.relpath(p, ROOT)
 
 
-def make_inputs(pinned: bool):
+def make_inputs(nbf, nocc):
     import jues.jl_b200 as jb
-    scale = jb.synth.counter_scale(NBF)           # same element variance as the dense generator; converges
-    Cao, Cav, eps = jb.synth.orbitals(NBF, NOCC, SEED)
-    g = jb.synth.counter_eri(NBF, SEED, scale)
-    if pinned:
-        import torch
-        t = torch.empty(g.size, dtype=torch.float64).pin_memory()
-        gp = t.numpy().reshape(g.shape, order="F")
-        gp[...] = g
-        return gp, Cao, Cav, eps, scale, t
-    return g, Cao, Cav, eps, scale, None
+    scale = jb.synth.counter_scale(nbf)           # same element variance as the dense generator; converges
+    Cao, Cav, eps = jb.synth.orbitals(nbf, nocc, SEED)
+    g = jb.synth.counter_eri(nbf, SEED, scale)
+    return g, Cao, Cav, eps
 
 
 class ClockSampler:
@@ -184,7 +196,7 @@ def fp64_peak():
         return 37.0, "fallback: DMMA issue-rate ceiling 148 SM x 64 FMA/clk x 1.965 GHz"
 
 
-def traffic_from_profile(name="ncu_dgemm_ladder_r01.json"):
+def traffic_from_profile(name):
     p = os.path.join(ROOT, "profiles", name)
     try:
         return float(json.load(open(p))["dram_bytes_per_launch"])
@@ -195,22 +207,78 @@ def traffic_from_profile(name="ncu_dgemm_ladder_r01.json"):
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle on host cores
 # ------------------------------------------------------------------------------------------
+def cpu_info():
+    model = None
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    threads = None
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max((d.get("num_threads", 0) for d in threadpool_info()), default=None)
+    except Exception:
+        pass
+    n = 4096
+    a = np.random.default_rng(0).standard_normal((n, n))
+    b = a.T.copy()
+    a @ b
+    t0 = time.perf_counter()
+    a @ b
+    dt = time.perf_counter() - t0
+    return {"cpu_model": model, "host_cores": os.cpu_count() or 1, "blas_threads": threads,
+            "dgemm_4096_tflops": 2.0 * n ** 3 / dt * 1e-12,
+            "env": {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS")}}
+
+
+def oracle_classes(nbf, nocc, real_inputs):
+    """The 15 arrays of make_rccsd_integrals (RCCSD.jl:117-142).  real_inputs: from the bench inputs through
+    the oracle's literal 15 transforms (timed).  Otherwise arrays of the right shapes filled with random
+    numbers of the right magnitude -- the sweep's cost does not depend on the values -- and ONE literal
+    transform (the <vv|vv> one, the most expensive of the 15) timed on a random AO tensor, the other 14
+    extrapolated by their flop counts."""
+    from oracle import jues_oracle as orc
+    fl = _flops()
+    o, v = nocc, nbf - nocc
+    if real_inputs:
+        g, Cao, Cav, eps = make_inputs(nbf, nocc)
+        t0 = time.perf_counter()
+        I = orc.make_rccsd_integrals(g, Cao, Cav)
+        return I, eps, time.perf_counter() - t0, "15 literal transforms timed"
+    rng = np.random.default_rng(1)
+    g = rng.standard_normal((nbf,) * 4)
+    C = rng.standard_normal((nbf, nbf)) / np.sqrt(nbf)
+    t0 = time.perf_counter()
+    orc.tei_transform(g, C[:, o:], C[:, o:], C[:, o:], C[:, o:])
+    t_v = time.perf_counter() - t0
+    del g
+    t_tr = t_v * fl.rccsd_transforms_ref(nbf, o, v) / fl.tei_flops_ref(nbf, v, v, v, v)
+    shape = {"o": o, "v": v}
+    I = {k: 1e-3 * rng.standard_normal(tuple(shape[c] for c in k)) for k in
+         ("vvvv", "ovvv", "vovv", "vvov", "vvvo", "oovv", "ovvo", "vovo", "ovov", "voov", "ooov", "oovo", "ovoo",
+          "vooo", "oooo")}
+    eps = np.concatenate([-1.0 - rng.random(o), 1.0 + rng.random(v)])
+    return I, eps, t_tr, f"<vv|vv> literal transform timed ({t_v:.1f} s) on a random AO tensor, the 15 extrapolated by flops"
+
+
 _ORACLE_STATE = {}
 
 
-def run_oracle_sample(n_iter: int):
-    """15 literal transforms (RCCSD.jl:117-142; done once per process and timed) + n_iter literal
-    sweeps at the bench config.  Returns (t_transform, t_iter_avg, energy_after_first_sweep)."""
+def run_oracle_sample(nbf, nocc, n_iter, real_inputs=True):
+    """Integral classes (once per process) + n_iter literal sweeps.  Returns (t_transform, t_iter_avg,
+    energy_after_first_sweep, how)."""
     from oracle import jues_oracle as orc
-    o, v = NOCC, NBF - NOCC
+    o, v = nocc, nbf - nocc
     st = _ORACLE_STATE
-    if not st:
-        g, Cao, Cav, eps, scale, _ = make_inputs(False)
-        t0 = time.perf_counter()
-        st["I"] = orc.make_rccsd_integrals(g, Cao, Cav)
-        st["t_tr"] = time.perf_counter() - t0
+    key = (nbf, nocc, real_inputs)
+    if st.get("key") != key:
+        st.clear()
+        st["key"] = key
+        st["I"], eps, st["t_tr"], st["how"] = oracle_classes(nbf, nocc, real_inputs)
         st["Dia"], st["D"] = orc.form_Dia(o, v, eps), orc.form_Dijab(o, v, eps)
-        del g
     I, Dia, D = st["I"], st["Dia"], st["D"]
     T1, T2 = np.zeros((o, v)), I["oovv"] / D
     e1 = None
@@ -221,37 +289,53 @@ def run_oracle_sample(n_iter: int):
         if k == 0:
             e1 = e
     t_it = (time.perf_counter() - t0) / max(n_iter, 1)
-    return st["t_tr"], t_it, e1
+    return st["t_tr"], t_it, e1, st["how"]
 
 
-def reference_arm(args, rank):
+def reference_arm(args, rank, world):
     if rank != 0:
         return
-    o, v = NOCC, NBF - NOCC
-    cores = os.cpu_count() or 1
-    t_tr_s, t_it_s = [], []
-    n_iter = 1
-    for step in range(args.warmup + args.steps):
-        t_tr, t_it, e = run_oracle_sample(n_iter)
-        if step >= args.warmup:
-            t_tr_s.append(t_tr); t_it_s.append(t_it)
-    t_tr, t_it = float(np.mean(t_tr_s)), float(np.mean(t_it_s))
-    F = flops_alg_rccsd(o, v)
-    t_call = t_tr + REF_MAXIT * t_it            # a complete do_rccsd: transforms + 40 sweeps
-    tf = F / t_it * 1e-12
-    e2e_tf = REF_MAXIT * F / t_call * 1e-12     # same numerator as the GPU arm: 40 sweeps of F_alg
+    fl = _flops()
+    world = max(world, args.gpus)      # the shape of the N-GPU arm, whichever way this arm was launched
+    nbf = NOCC + WEAK_NVIR.get(world, 100)
+    o, v = NOCC, nbf - NOCC
+    info = cpu_info()
+    real = world == 1           # N=1: the bench inputs themselves (energy cross-check with the GPU arm)
+    budget_s = float(os.environ.get("BENCH_REF_BUDGET_S", "240"))
+    t_start = time.perf_counter()
+    t_tr, t_first, e1, how = run_oracle_sample(nbf, NOCC, 1, real)      # first sweep = warm-up
+    t_it_s = []
+    want = args.warmup + args.steps
+    for step in range(want):
+        if time.perf_counter() - t_start + t_first > budget_s and len(t_it_s) >= 1:
+            break
+        _, t_it, _, _ = run_oracle_sample(nbf, NOCC, 1, real)
+        t_it_s.append(t_it)
+    timed = t_it_s[min(args.warmup, len(t_it_s) - 1):] or t_it_s
+    t_it = float(np.mean(timed))
+    F_ref = fl.rccsd_iter_ref(o, v)                 # the flops this algorithm executes per sweep
+    F_tr = fl.rccsd_transforms_ref(nbf, o, v)
+    t_call = t_tr + REF_MAXIT * t_it                # a complete do_rccsd: transforms + 40 sweeps
+    tf = F_ref / t_it * 1e-12
+    e2e_tf = (F_tr + REF_MAXIT * F_ref) / t_call * 1e-12
+    sample = (f"{how}; {len(timed)} literal sweep(s) timed ({t_it:.2f} s each, {len(t_it_s) - len(timed)} warm-up) "
+              f"within a {budget_s:.0f} s budget; do_rccsd extrapolated to {REF_MAXIT} sweeps")
     line = {
         "impl": "reference", "metric": "rccsd_iteration_fp64_tflops", "value": tf, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_it * 1e3,
-        "s_per_iteration": t_it, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "s_per_iteration": t_it, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"RCCSD nbf={NBF} nocc={NOCC} nvir={v} (BASELINE config 3), synthetic counter-based ERIs",
+        "config": {"workload": f"RCCSD nbf={nbf} nocc={NOCC} nvir={v}"
+                               + (" (BASELINE config 3)" if world == 1 else " (config 3 grown for weak scaling, the GPU arm's shape)")
+                               + ", synthetic ERIs",
                    "algorithm": "reference literal: 15 tei_transforms + sweeps with materialised Wabef (numpy/OpenBLAS port)",
-                   "note": "the reference's CPU path does not shard: for every --gpus N it is timed on the 1-GPU workload "
-                           "(BASELINE config 3); the metric is F_alg-normalised TFLOP/s, comparable across the weak-scaling shapes"},
-        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port",
-                         "sample": f"15 literal transforms ({t_tr:.2f} s) + {n_iter} literal sweep(s) ({t_it:.2f} s each) "
-                                   f"per step; do_rccsd extrapolated to {REF_MAXIT} sweeps"},
+                   "flops_executed_per_sweep": F_ref, "F_alg_per_sweep": fl.rccsd_iter_alg(o, v),
+                   "alg_normalised_tflops": fl.rccsd_iter_alg(o, v) / t_it * 1e-12,
+                   "note": "value = flops this algorithm executes (F_ref) / seconds; the CPU path does not shard, so "
+                           "rank 0 alone runs the whole workload of the N-GPU arm"},
+        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": info["blas_threads"] or info["host_cores"],
+                         "kind": "port", "sample": sample, "s_per_iteration": t_it, "s_transforms": t_tr,
+                         "energy_after_first_sweep": e1 if real else None, **info},
         "e2e": {"value": e2e_tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "s_per_do_rccsd": t_call, "s_per_iteration": t_call / REF_MAXIT},
     }
@@ -261,32 +345,128 @@ def reference_arm(args, rank):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+def split_sweeps(ph):
+    """Phases of a traced call -> list of per-sweep lists [(name, ms)], closed by each cc.iteration entry."""
+    out, cur = [], []
+    for k, ms in ph:
+        if k == "cc.iteration":
+            out.append((ms, cur))
+            cur = []
+        elif k.startswith("gemm ") or k.startswith("cc.comm.") or k.startswith("cc.part."):
+            cur.append((k, ms))
+    return out
+
+
+def insitu_roofline(ctx, jb, wdev, peak, peak_src, world, nbf):
+    """Dominant GEMM of the sweep, its launch duration measured inside the sweep."""
+    ctx.set_trace(2)
+    try:
+        jb.RCCSD.do_rccsd(wdev, ctx=ctx, _maxit=5)
+        sweeps = split_sweeps(ctx.phases())
+    finally:
+        ctx.set_trace(0)
+    sweeps = sweeps[2:] or sweeps           # the first sweeps build lazily created operand copies
+    tot = {}
+    for ms_sweep, items in sweeps:
+        for k, ms in items:
+            if k.startswith("gemm "):
+                tot.setdefault(k, []).append(ms)
+    name = max(tot, key=lambda k: sum(tot[k]))
+    M, N, K, B = (int(x) for x in name.split()[1].split("x"))
+    per_sweep = len(tot[name]) / len(sweeps)
+    ms_launch = float(np.mean(tot[name]))
+    ms_sweep = float(np.mean([s for s, _ in sweeps]))
+    ach = 2.0 * M * N * K * B / ms_launch * 1e-9
+    iso = B * ctx.gemm_bench("T" if (M == N == K) else "N", "N", M, N, K, reps=5) if B <= 2 else None
+    comm = {}
+    for _, items in sweeps:
+        for k, ms in items:
+            if k.startswith("cc.comm."):
+                comm[k] = comm.get(k, 0.0) + ms / len(sweeps)
+    all_gemm = sum(sum(v) for v in tot.values()) / len(sweeps)
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": traffic_from_profile("ncu_dgemm_ring_r01.json") if (world == 1 and nbf == 120 and M == 2000) else None,
+            "kernel": "jues::gemm::dgemm_tma_dmma (FP64 DMMA.8x8x4 fed by TMA)",
+            "shape": f"M={M} N={N} K={K} batch={B} ({per_sweep:.0f} launches per sweep)",
+            "ms_per_launch": ms_launch, "how": "CUDA-event pair around every launch inside traced eager sweeps",
+            "share_of_sweep": ms_launch * per_sweep / ms_sweep, "all_gemms_share_of_sweep": all_gemm / ms_sweep,
+            "traced_sweep_ms": ms_sweep, "isolated_ms_per_launch": iso,
+            "isolated_tflops": (2.0 * M * N * K * B / iso * 1e-9) if iso else None,
+            "peak_source": peak_src}, comm
+
+
+def large_block(ctx, jb, dist, torch, world, rank, peak):
+    """RCCSD at the shapes the metric's targets are quoted on, storage-less synthetic AO tensor."""
+    res = {}
+    todo = [("strong", *LARGE["strong"])] + ([("c5", *LARGE["c5"])] if world == 8 else [])
+    for tag, nbf, nocc in todo:
+        try:
+            v = nbf - nocc
+            Cao, Cav, eps = jb.synth.orbitals(nbf, nocc, SEED)
+            g = jb.DeviceFourTensor.synth_eri(nbf, seed=SEED, ctx=ctx, virtual=True)
+            w = jb.Wfn(nocc, v, eps, Cao, Cav, g)
+            hist = []
+            ctx.set_trace(1)
+            try:
+                jb.RCCSD.do_rccsd(w, ctx=ctx, _maxit=3, _e_hist=hist)
+            finally:
+                ctx.set_trace(0)
+            ph, c = ctx.phases(), ctx.counters()
+            it = [ms for k, ms in ph if k == "cc.iteration"]
+            gf = [ms for k, ms in ph if k == "cc.iteration.gflop"]
+            tr = [ms for k, ms in ph if k == "cc.transform"][0]
+            ms_it = float(np.median(it[1:]))
+            comm_ms = sum(ms for k, ms in ph if k.startswith("cc.comm.")) / len(it)
+            exch_ms = sum(ms for k, ms in ph if k == "tei.exchange")
+            tr_flops = c["gemm_flops"] - sum(gf) * 1e9
+            vals = [ms_it, tr, comm_ms, float(np.median(gf)) * 1e9, tr_flops]
+            if dist is not None:
+                t = torch.tensor(vals[:3], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                s = torch.tensor(vals[3:], dtype=torch.float64, device="cuda")
+                dist.all_reduce(s, op=dist.ReduceOp.SUM)
+                vals = [float(x) for x in t] + [float(x) for x in s]
+            ms_it, tr, comm_ms, fl_it, fl_tr = vals
+            res[tag] = {"workload": f"RCCSD nbf={nbf} nocc={nocc} nvir={v}" + (" (BASELINE config 5)" if tag == "c5" else "")
+                                    + f", generated AO integrals, {world} GPU(s)", "scaling": "strong",
+                        "s_per_iteration": ms_it * 1e-3, "executed_tflops_per_gpu": fl_it / (ms_it * 1e-3) * 1e-12 / world,
+                        "frac_of_fp64_peak_per_gpu": fl_it / (ms_it * 1e-3) * 1e-12 / world / peak,
+                        "transform_s": tr * 1e-3, "transform_tflops_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world,
+                        "transform_frac_of_fp64_peak_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world / peak,
+                        "comm_ms_per_sweep": comm_ms, "transform_exchange_ms_overlapped": exch_ms,
+                        "e_hist": hist, "peak_device_GB": c["bytes_peak"] / 1e9}
+            g.free()
+        except Exception as ex:     # noqa: BLE001
+            res[tag] = {"error": str(ex)[:300]}
+    return res
+
+
 def gpu_arm(args, rank, world):
     import torch
     import jues.jl_b200 as jb
+    fl = _flops()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", rank=rank, world_size=world)
-    global NBF
     # weak scaling: nocc fixed, nvir grows so that F_alg per GPU stays (approximately) that of the
     # 1-GPU workload (BASELINE config 3); nvir is a multiple of 2*N so the slabs need no padding
-    NBF = NOCC + WEAK_NVIR.get(world, 100)
-    o, v = NOCC, NBF - NOCC
+    nbf = NOCC + WEAK_NVIR.get(world, 100)
+    o, v = NOCC, nbf - NOCC
     ctx = jb.Context(local)
     if world > 1:
         ctx.init_dist(rank, world)          # NCCL communicator inside the library (id via torch.distributed)
-    scale = jb.synth.counter_scale(NBF)
-    Cao, Cav, eps = jb.synth.orbitals(NBF, NOCC, SEED)
-    gdev = jb.DeviceFourTensor.synth_eri(NBF, seed=SEED, scale=scale, ctx=ctx)   # inputs resident in HBM
+    scale = jb.synth.counter_scale(nbf)
+    Cao, Cav, eps = jb.synth.orbitals(nbf, NOCC, SEED)
+    gdev = jb.DeviceFourTensor.synth_eri(nbf, seed=SEED, scale=scale, ctx=ctx)   # inputs resident in HBM
     # the same tensor in pinned host memory for the end-to-end leg (copied back from the device:
     # bit-identical to synth.counter_eri, without minutes of numpy at the larger shapes)
-    keep = torch.empty(NBF ** 4, dtype=torch.float64).pin_memory()
-    g = keep.numpy().reshape((NBF,) * 4, order="F")
-    for s0 in range(0, NBF, 16):
-        s1 = min(NBF, s0 + 16)
+    keep = torch.empty(nbf ** 4, dtype=torch.float64).pin_memory()
+    g = keep.numpy().reshape((nbf,) * 4, order="F")
+    for s0 in range(0, nbf, 16):
+        s1 = min(nbf, s0 + 16)
         g[:, :, :, s0:s1] = gdev[:, :, :, s0:s1]
     wdev = jb.Wfn(NOCC, v, eps, Cao, Cav, gdev)
     whost = jb.Wfn(NOCC, v, eps, Cao, Cav, g)
@@ -322,19 +502,20 @@ def gpu_arm(args, rank, world):
     launches_step = ((cnt["gemm_launches"] - c0["gemm_launches"]) + (cnt["aux_launches"] - c0["aux_launches"])) \
         / (args.warmup + args.steps)
 
+    peak, peak_src = fp64_peak()
     # ---- the 4-index transform part of the metric -------------------------------------------------
-    # (a) the integral classes of the CC run (sharded: every rank transforms its virtual slab);
-    #     flops and time of the zero-sweep call above
+    # (a) every integral class of the CC run from ONE sharded pass (flops and time of the zero-sweep call)
     tr0_ms = [ms for k, ms in ctx.phases() if k == "cc.transform"][0]
     tr_flops = c0["gemm_flops"]
     if dist is not None:
-        tt_ = torch.tensor([tr_flops, -tr0_ms], dtype=torch.float64, device="cuda")
+        tt_ = torch.tensor([tr_flops, tr0_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt_[0:1], op=dist.ReduceOp.SUM)
-        dist.all_reduce(tt_[1:2], op=dist.ReduceOp.MIN)
-        tr_flops, tr0_ms = float(tt_[0]), -float(tt_[1])
-    tei = {"cc_classes": {"workload": f"7 MO classes of RCCSD (<oo|vv>,<ov|ov>,<oo|oo>,<oo|ov>,<vv|vv>,<vv|ov>,<vo|vv>) "
-                                      f"nbf={NBF}, virtual slab per rank", "ms": tr0_ms,
-                          "tflops": tr_flops / tr0_ms * 1e-9}}
+        dist.all_reduce(tt_[1:2], op=dist.ReduceOp.MAX)
+        tr_flops, tr0_ms = float(tt_[0]), float(tt_[1])
+    tei = {"cc_classes": {"workload": f"all MO integral classes of RCCSD from one sharded pass over gao (device-resident), "
+                                      f"nbf={nbf}, last index split over {world} rank(s)", "ms": tr0_ms,
+                          "flops_executed": tr_flops, "tflops": tr_flops / tr0_ms * 1e-9,
+                          "frac_of_fp64_peak": tr_flops / tr0_ms * 1e-9 / (peak * world)}}
     # (b) full tei_transform(gao, C) (all four indices, 8 N^5 flop) -- single GPU
     if world == 1:
         Cfull = np.asfortranarray(np.hstack([Cao, Cav]))
@@ -342,8 +523,9 @@ def gpu_arm(args, rank, world):
             out = jb.tei_transform(gdev, Cfull, "bench", ctx=ctx)
             out.free()
         tt_ms = [ms for k, ms in ctx.phases() if k == "tei.transform"][0]
-        tei["full"] = {"workload": f"tei_transform(gao, C) nbf={NBF} (all four indices, 8 N^5 flop)", "ms": tt_ms,
-                       "tflops": ctx.counters()["gemm_flops"] / tt_ms * 1e-9}
+        tei["full"] = {"workload": f"tei_transform(gao, C) nbf={nbf} (all four indices, 8 N^5 flop)", "ms": tt_ms,
+                       "tflops": ctx.counters()["gemm_flops"] / tt_ms * 1e-9,
+                       "frac_of_fp64_peak": ctx.counters()["gemm_flops"] / tt_ms * 1e-9 / peak}
 
     # ---- e2e: one complete do_rccsd through the C ABI from pinned HOST buffers ----------------
     e2e_t = []
@@ -355,29 +537,14 @@ def gpu_arm(args, rank, world):
         e2e_t.append(time.perf_counter() - t0)
     t_call = min(e2e_t)
     c_full = ctx.counters()
+    e2e_phases = {}
+    for k, ms in ctx.phases():
+        if k in ("cc.transform", "cc.static", "total"):
+            e2e_phases[k] = ms
     clocks = sampler.stop()
 
-    # ---- roofline of the dominant kernel, timed live (CUDA events on the library's stream) ----
-    if world == 1:
-        # one rank: the pp-ladder runs in the packed symmetric/antisymmetric pair space (half its flops),
-        # which leaves the seven ring products (ov x ov)(ov x ov) as the largest share of the sweep
-        # (41 % of its kernel time, profiles/ncu_launches_rccsd_sweep_r01b.csv)
-        M = Nn = K = o * v
-        tA, shape, prof = "T", f"ring GEMM (ov x ov)(ov x ov) M=N=K={M}", "ncu_dgemm_ring_r01.json"
-    else:
-        # several ranks: this rank's column block of the packed (symmetric/antisymmetric) pp-ladder,
-        # tau+-(ij,(ef)) x W+-((ef),(ab)): two such products per sweep in one batched launch
-        M, Nn, K = o * o, (v // world) * (v // 2 + 1), v * (v + 1) // 2
-        tA, shape, prof = "N", f"packed pp-ladder GEMM M={M} N={Nn} K={K} (x2 per sweep)", "ncu_dgemm_ladder_r01.json"
-    ms_gemm = ctx.gemm_bench(tA, "N", M, Nn, K, reps=5)
-    peak, peak_src = fp64_peak()
-    ach = 2.0 * M * Nn * K / ms_gemm * 1e-9
-    roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                # measured DRAM bytes per launch (ncu --set full) exist for the 1-GPU shape only
-                "traffic": traffic_from_profile(prof) if (world == 1 and NBF == 120) else None,
-                "kernel": "jues::gemm::dgemm_tma_dmma (FP64 DMMA.8x8x4 fed by TMA)",
-                "shape": shape, "ms_per_launch": ms_gemm, "peak_source": peak_src,
-                "sweep_frac_of_peak": flops_step / (ms_step * 1e-3) * 1e-12 / peak}
+    # ---- roofline of the dominant kernel, measured inside the sweep ---------------------------------
+    roofline, comm_ms = insitu_roofline(ctx, jb, wdev, peak, peak_src, world, nbf)
 
     # ---- max over ranks -----------------------------------------------------------------------
     comm = ctx.comm_counters()
@@ -388,27 +555,47 @@ def gpu_arm(args, rank, world):
         fs = torch.tensor([flops_step, c_full["gemm_flops"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(fs, op=dist.ReduceOp.SUM)      # whole-job executed flops
         flops_step, c_full["gemm_flops"] = float(fs[0]), float(fs[1])
-        roofline["sweep_frac_of_peak"] = flops_step / (ms_step * 1e-3) * 1e-12 / (peak * world)
+    roofline["sweep_frac_of_peak"] = flops_step / (ms_step * 1e-3) * 1e-12 / (peak * world)
+    roofline["comm_ms_per_traced_sweep"] = comm_ms
+
+    # ---- the configurations the targets are quoted on ------------------------------------------------
+    large = None
+    if not args.no_large:
+        large = large_block(ctx, jb, dist, torch, world, rank, peak)
 
     if rank != 0:
-        return
+        return 0
+    # ---- parity: the timed run's energies against the committed oracle trace ----------------------
+    gold, gold_path = golden_trace(nbf, NOCC)
+    if gold is None:
+        parity = {"status": "unpinned", "golden": gold_path, "tol": E_TOL,
+                  "note": "no committed oracle trace for this shape"}
+    else:
+        ref = np.asarray(gold["e_hist"])
+        n = min(len(ref), len(hist))
+        d_run = float(np.abs(np.asarray(hist[:n]) - ref[:n]).max())
+        d_e2e = float(abs(e_host - ref[REF_MAXIT])) if len(ref) > REF_MAXIT else None
+        worst = max(d_run, d_e2e or 0.0)
+        parity = {"status": "ok" if worst <= E_TOL else "FAILED", "max_abs_dE": worst, "tol": E_TOL,
+                  "max_abs_dE_timed_run": d_run, "sweeps_compared": n, "abs_dE_e2e_40_sweeps": d_e2e,
+                  "golden": gold_path, "oracle": "oracle/jues_oracle.py (literal RCCSD.jl:150-289), tests/golden/make_bench_golden.py"}
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only), bounded sample ------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        t_tr, t_it, e_cpu = run_oracle_sample(1)
-        cpu = {"value": flops_alg_rccsd(o, v) / t_it * 1e-12, "unit": "TFLOP/s", "cores": os.cpu_count() or 1,
+        t_tr, t_it, e_cpu, how = run_oracle_sample(nbf, NOCC, 1, True)
+        info = cpu_info()
+        cpu = {"value": fl.rccsd_iter_ref(o, v) / t_it * 1e-12, "unit": "TFLOP/s",
+               "cores": info["blas_threads"] or info["host_cores"],
                "kind": "port", "s_per_iteration": t_it, "s_transforms": t_tr,
                "sample": f"oracle (numpy/OpenBLAS port of the reference's literal algorithm): 15 transforms "
-                         f"({t_tr:.1f} s) + 1 sweep ({t_it:.1f} s) at nbf={NBF} nocc={NOCC}",
-               "energy_check": abs(e_cpu - hist[1]) if len(hist) > 1 else None}
+                         f"({t_tr:.1f} s) + 1 sweep ({t_it:.1f} s) at nbf={nbf} nocc={NOCC}; value = F_ref / s",
+               "energy_check": abs(e_cpu - hist[1]) if len(hist) > 1 else None, **info}
     # ---- the callers either side of the path, same inputs, one GPU: AutoRCCSD to
     #      |dE|, rms <= 1e-10 with the (T) correction, through the C ABI from host buffers.  Extra keys only;
     #      never allowed to break the line.
     next_rows = None
     if world == 1 and not args.no_next_rows:
         try:
-            from importlib import import_module
-            fl = import_module("jues.jl_b200.flops")
             t0 = time.perf_counter()
             hao = jb.synth.core_hamiltonian(g, Cao, Cav, eps)      # host plumbing: makes (C, eps) the RHF solution
             t_h = time.perf_counter() - t0
@@ -425,34 +612,40 @@ def gpu_arm(args, rank, world):
                          "ms_per_sweep_median": float(np.median(sw)) if sw else None,
                          "fock_build_ms": [ms for k, ms in pa if k == "fock.build"],
                          "triples_ms": tr[0] if tr else None,
-                         "triples_tflops": fl.pt_flops(NOCC, v) / (tr[0] * 1e-3) * 1e-12 if tr else None}
+                         "triples_tflops": fl.pt_flops(NOCC, v) / (tr[0] * 1e-3) * 1e-12 if tr else None,
+                         "triples_frac_of_fp64_peak": fl.pt_flops(NOCC, v) / (tr[0] * 1e-3) * 1e-12 / peak if tr else None}
         except Exception as ex:     # noqa: BLE001
             next_rows = {"error": str(ex)[:300]}
-    F_alg = flops_alg_rccsd(o, v)
+    F_alg, F_ref = fl.rccsd_iter_alg(o, v), fl.rccsd_iter_ref(o, v)
+    s_it = ms_step * 1e-3
+    h2d = int(g.nbytes // world + Cao.nbytes + Cav.nbytes + eps.nbytes)
     line = {
-        # algorithmic FP64 throughput: F_alg per sweep / seconds per sweep (both arms use F_alg);
-        # the flops the kernels actually executed (<= F_alg) are in config and roofline
-        "metric": "rccsd_iteration_fp64_tflops", "value": F_alg / (ms_step * 1e-3) * 1e-12,
+        # executed FP64 throughput of the whole job: flops the GEMM kernels of all ranks ran per sweep / s
+        "metric": "rccsd_iteration_fp64_tflops", "value": flops_step / s_it * 1e-12,
         "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "s_per_iteration": ms_step * 1e-3, "higher_is_better": True,
+        "ms_per_step": ms_step, "s_per_iteration": s_it, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"RCCSD nbf={NBF} nocc={NOCC} nvir={v}"
+        "config": {"workload": f"RCCSD nbf={nbf} nocc={NOCC} nvir={v}"
                                + (" (BASELINE config 3)" if world == 1 else
-                                  f" (config 3 grown for weak scaling: F_alg = {F_alg / flops_alg_rccsd(NOCC, 100):.2f} x the 1-GPU workload)")
+                                  f" (config 3 grown for weak scaling: F_alg = {F_alg / fl.rccsd_iter_alg(NOCC, 100):.2f} x the 1-GPU workload)")
                                + f", synthetic counter-based ERIs seed={SEED}",
-                   "parallelism": f"virtual-index slabs over {world} GPU(s), NCCL all-gather of H and T2 + one all-reduce per sweep"
-                                  if world > 1 else "single GPU",
+                   "parallelism": f"virtual-index slabs over {world} GPU(s): NCCL all-gathers of the ladder blocks, H and T2 + one "
+                                  f"all-reduce per sweep; point-to-point exchange in the transform" if world > 1 else "single GPU",
                    "collectives_per_call": comm,
                    "step": "one RCCSD sweep (intermediates + T1 + T2 + energy) on device-resident data",
-                   "l2": "inputs larger than L2 (<vv|vv> >= 0.8 GB per GPU, amplitudes/intermediates >= 32 MB each, re-streamed every sweep)",
-                   "flops_executed_per_sweep": flops_step, "F_alg_per_sweep": F_alg, "F_ref_per_sweep": flops_ref_rccsd(o, v)},
+                   "l2": "inputs larger than L2 (<vv|vv> >= 0.4 GB per GPU, amplitudes/intermediates >= 32 MB each, re-streamed every sweep)",
+                   "flops_executed_per_sweep": flops_step, "F_alg_per_sweep": F_alg, "F_ref_per_sweep": F_ref,
+                   "alg_normalised_tflops": F_alg / s_it * 1e-12, "ref_normalised_tflops": F_ref / s_it * 1e-12,
+                   "value_is": "flops_executed_per_sweep (all ranks) / s_per_iteration"},
         "tei_transform": tei,
-        "e2e": {"value": REF_MAXIT * F_alg / t_call * 1e-12, "unit": "TFLOP/s",
+        "e2e": {"value": c_full["gemm_flops"] / t_call * 1e-12, "unit": "TFLOP/s",
                 "flops_executed": c_full["gemm_flops"],
-                "h2d_bytes_per_step": int(g.nbytes + Cao.nbytes + Cav.nbytes + eps.nbytes),
-                "d2h_bytes_per_step": int(8 * (REF_MAXIT + 2)),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * (REF_MAXIT + 2)),
                 "s_per_do_rccsd": t_call, "s_per_iteration": t_call / REF_MAXIT,
-                "what": "jues_b200_rccsd(host gao, Cao, Cav, eps, maxit=40): H2D + transform + 40 sweeps + energies D2H"},
+                "alg_normalised_tflops": REF_MAXIT * F_alg / t_call * 1e-12,
+                "phases_ms_rank0": e2e_phases,
+                "what": "jues_b200_rccsd(host gao, Cao, Cav, eps, maxit=40): H2D of this rank's 1/N of gao + one-pass "
+                        "transform + 40 sweeps + energies D2H; value = executed flops (transform + sweeps, all ranks) / s"},
         "gpu_launches": int(round(launches_step)),
         "ms_each_step_rank0": [round(x, 3) for x in it_ms],
         # host clock (ms since the first sweep was issued) at which each sweep had been handed to the
@@ -460,13 +653,16 @@ def gpu_arm(args, rank, world):
         "host_issue_ms_rank0": [round(ms, 3) for k, ms in ph if k == "cc.iteration.host_ms"],
         "graph_replayed_sweeps": int(sum(ms for k, ms in ph if k == "cc.graph_launches")),
         "roofline": roofline,
+        "parity": parity,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "energy": {"E_ccsd_after_timed_sweeps": e, "E_ccsd_40_sweeps_e2e": e_host},
         "integral_transform_ms": tr_ms,
+        "large": large,
         "next_rows": next_rows,
     }
     print(json.dumps(line), flush=True)
+    return 0 if parity["status"] != "FAILED" else 3
 
 
 def main():
@@ -477,6 +673,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the AutoRCCSD(T) extra keys")
+    ap.add_argument("--no-large", action="store_true", help="skip the nbf=300 / config-5 block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -487,12 +684,12 @@ def main():
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
-        reference_arm(args, rank)
-        return
+        reference_arm(args, rank, world)
+        return 0
     if args.warmup < 3:
         args.warmup = 3
-    gpu_arm(args, rank, world)
+    return gpu_arm(args, rank, world)
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main() or 0)

@@ -223,6 +223,10 @@ typedef struct {
     double ms;
 } jues_b200_phase;
 int jues_b200_get_phases(jues_ctx* ctx, jues_b200_phase* out, int cap);
+/* Trace level of the following calls: 0 coarse phases; 1 also cc.part.*, cc.comm.*, tei.* regions
+ * (the JUES_B200_TRACE=1 default); 2 also one CUDA-event pair around every DGEMM launch, reported as
+ * phase "gemm MxNxKxbatch" (in-situ launch durations).  Tracing runs the sweeps eagerly (no graph replay). */
+int jues_b200_set_trace(jues_ctx* ctx, int level);
 int jues_b200_get_counters(jues_ctx* ctx, double* gemm_flops, int64_t* gemm_launches,
                            int64_t* aux_launches, int64_t* bytes_peak);
 /* NCCL collectives issued by the last call and the bytes this rank received in them.           */

@@ -158,6 +158,10 @@ class Context:
         self._lib.jues_b200_get_phases(self._h, buf, n)
         return [(buf[i].name.decode(), buf[i].ms) for i in range(n)]
 
+    def set_trace(self, level: int):
+        """0 coarse phases, 1 regions (cc.part.*, cc.comm.*, tei.*), 2 every DGEMM launch ("gemm MxNxKxb")."""
+        self._check(self._lib.jues_b200_set_trace(self._h, int(level)))
+
     def counters(self):
         fl = C.c_double()
         gl, al, bp = C.c_int64(), C.c_int64(), C.c_int64()

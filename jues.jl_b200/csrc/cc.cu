@@ -446,7 +446,8 @@ struct CC {
     }
 
     void sweep() {
-        static const bool off = getenv("JUES_B200_NO_GRAPH") != nullptr || getenv("JUES_B200_TRACE") != nullptr;
+        static const bool no_graph = getenv("JUES_B200_NO_GRAPH") != nullptr;
+        const bool off = no_graph || ctx->trace > 0;
         // the first sweep runs eagerly: it builds every lazily created operand copy / kernel attribute
         if (off || !use_graphs || !graph_ok || ctx->nranks != 1 || eager_sweeps < 1) {
             iterate();

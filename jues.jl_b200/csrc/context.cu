@@ -43,6 +43,7 @@ extern "C" int jues_b200_init(jues_ctx** out, int device) {
         ctx->sm_count = prop.multiProcessorCount;
         if (const char* mb = getenv("JUES_B200_BIG_MB")) ctx->big_bytes = (size_t)std::max(1, atoi(mb)) << 20;
         ctx->sync_comm = getenv("JUES_B200_SYNC_COMM") != nullptr;
+        if (const char* tr = getenv("JUES_B200_TRACE")) ctx->trace = std::max(1, atoi(tr));
         JUES_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         JUES_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
         {   // keep freed blocks in the stream-ordered pool (all work of a context is on one stream)
@@ -90,6 +91,12 @@ extern "C" void jues_b200_finalize(jues_ctx* ctx) {
 extern "C" const char* jues_b200_last_error(jues_ctx* ctx) {
     if (!ctx) return g_init_error.c_str();
     return ctx->last_error.c_str();
+}
+
+extern "C" int jues_b200_set_trace(jues_ctx* ctx, int level) {
+    if (!ctx || level < 0 || level > 2) return JUES_B200_EINVAL;
+    ctx->trace = level;
+    return JUES_B200_OK;
 }
 
 extern "C" int jues_b200_get_phases(jues_ctx* ctx, jues_b200_phase* out, int cap) {

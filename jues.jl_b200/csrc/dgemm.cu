@@ -175,11 +175,9 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
 
     int smem = 0;
     KernelFn fn = pick_kernel(a_kc, b_kc, cfg, &smem);
-    static std::map<void*, bool> attr_set;  // per process; kernels are per-device functions
-    if (!attr_set[(void*)fn]) {
+    // the attribute is per (device, kernel): remembered in the context, not in a process-wide static
+    if (ctx->smem_attr_done.insert((const void*)fn).second)
         JUES_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set[(void*)fn] = true;
-    }
     const int threads = (c.BM / c.WM) * (c.BN / c.WN) * 32 + 32;
     p.total_tiles = total;
     // persistent CTAs (one per SM) once there is more than ~a wave of tiles; otherwise one CTA per tile
@@ -189,7 +187,17 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
     // cost ~1-3 % on long-K tiles (static tile assignment, extra live registers), so: short K only.
     const bool persistent = persistent_gemm() && kt_per_split <= 32 && total > sms;
     const long long grid = persistent ? sms : total;
-    fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(mapA, mapB, p);
+    {
+        Timer* tk = nullptr;
+        if (ctx->trace >= 2) {
+            char nm[48];
+            snprintf(nm, sizeof nm, "gemm %lldx%lldx%lldx%lld", (long long)g.M, (long long)g.N, (long long)g.K,
+                     (long long)g.batch);
+            tk = new Timer(ctx, nm);
+        }
+        fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(mapA, mapB, p);
+        delete tk;
+    }
     JUES_CUDA(cudaGetLastError());
     ctx->stats.gemm_flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch;
     ctx->stats.gemm_launches += 1;

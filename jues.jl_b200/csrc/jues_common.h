@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <set>
 #include <stdexcept>
 #include <chrono>
 
@@ -102,6 +103,11 @@ struct jues_ctx {
     // threshold of DBuf, JUES_B200_SYNC_COMM=1 drains the stream around every collective
     size_t big_bytes = size_t(64) << 20;
     bool sync_comm = false;
+    // 0: coarse phases only; 1: cc.part.* / cc.comm.* / tei.* regions (JUES_B200_TRACE=1 or
+    // jues_b200_set_trace); 2: additionally one event pair around EVERY DGEMM launch, recorded as
+    // "gemm MxNxKxbatch" (in-situ kernel durations for the roofline; sweeps run eagerly while tracing)
+    int trace = 0;
+    std::set<const void*> smem_attr_done;   // kernels whose dynamic shared-memory limit was raised on this device
     // per-sweep amplitude capture (tests)
     jues_b200_amp_cb amp_cb = nullptr;
     void* amp_user = nullptr;
@@ -273,8 +279,7 @@ struct StreamScope {
 struct TraceTimer {
     Timer* t = nullptr;
     TraceTimer(jues_ctx* ctx, const char* name) {
-        static const bool on = getenv("JUES_B200_TRACE") != nullptr;
-        if (on) t = new Timer(ctx, name);
+        if (ctx->trace > 0) t = new Timer(ctx, name);
     }
     ~TraceTimer() { delete t; }
 };

@@ -28,6 +28,13 @@
 
 namespace jues {
 
+// fused assemble + energy kernel (48 v^3 instead of 80 v^3 bytes per triple); JUES_B200_PT_FUSED=0 selects the
+// two-kernel path
+static bool pt_use_fused() {
+    const char* e = getenv("JUES_B200_PT_FUSED");
+    return e ? atoi(e) != 0 : false;
+}
+
 namespace {
 
 template <int THREADS>
@@ -224,6 +231,7 @@ double pt_dev(jues_ctx* ctx, const PtInputs& in, double* scratch, size_t scratch
     DBuf slots(ctx, (size_t)nslots + 1);
     slots.zero();
     int64_t slot = 0, pair = 0;
+    const bool fused = pt_use_fused();
     for (int64_t i = 0; i < nocc; ++i) {
         for (int64_t j = 0; j <= i; ++j, ++pair) {
             if (pair % ctx->nranks != ctx->rank) continue;
@@ -239,7 +247,7 @@ double pt_dev(jues_ctx* ctx, const PtInputs& in, double* scratch, size_t scratch
                 x_blocks(ctx, in, j, 0, i, 0, k0, 1, kb, X.p + 5 * fam);   // X(j,i,k)
                 delete tg;
                 TraceTimer ta(ctx, "pt.assemble+energy");
-                if (getenv("JUES_B200_PT_FUSED") != nullptr) {
+                if (fused) {
                     PtFusedArgs fa{X.p, in.Vv, in.t1, in.eo, in.ev, (int)o, (int)v, (int)i, (int)j, (int)k0, (int)kb};
                     const long long items = v * (v + 1) / 2 * kb;
                     const int fgrid = (int)std::min<long long>(std::min<long long>(items, (long long)ctx->sm_count * 32),

@@ -612,12 +612,9 @@ void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const dou
                      int64_t v, int64_t b0, int64_t vs) {
     const size_t smem = (size_t)o * (o + 1) * sizeof(double);
     JUES_REQUIRE(smem <= 200 * 1024, "residual_finish: nocc too large for the shared-memory slab");
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (ctx->smem_attr_done.insert((const void*)residual_finish_kernel).second)
         JUES_CUDA(cudaFuncSetAttribute(residual_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        200 * 1024));
-        attr_done = true;
-    }
     long long blocks = (long long)v * vs;
     if (blocks == 0) return;
     const long long cap = (long long)ctx->sm_count * 16;
