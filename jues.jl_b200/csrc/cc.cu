@@ -246,6 +246,8 @@ struct CC {
         if (had_graph) cudaDeviceGraphMemTrim(ctx->device);   // give the graphs' memory back to the device
         ctx->perm_cache = nullptr;
         pcache.clear();
+        if (ctx->arena == &arena) ctx->arena = nullptr;        // members that still hold arena blocks just drop them
+        if (ev_fork) { cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
     }
 
     double energy() { return cc_energy(ctx, V.p(), T2.p(), singles ? T1.p() : nullptr, o, v); }
@@ -271,16 +273,17 @@ struct CC {
         const Ten t = T1, T = T2;
         const Ten tS = last_slab(t, b0, vs), T_S = last_slab(T, b0, vs);
         const Ten V_S = last_slab(V, b0, vs), Vt_S = last_slab(Vt, b0, vs), J_S = last_slab(J, b0, vs);
-        DTen tau, tauh, Tt;
+        // every amplitude-derived operand of the sweep in one pass over T2:
+        // Tt = 2T - T(ji), tau = T + tt, tauh = T + tt/2, Tp2 = T + 2tt
+        DTen tau, tauh, Tt, Tp2;
         Tt.alloc(ctx, o, o, v, v);
-        axpby(ctx, n2, 2.0, T.p, 0.0, Tt.p());
-        permute_axpby(ctx, -1.0, T, "ijab", 1.0, Tt, "jiab");           // Tt = 2T - T(ji)
         Ten tauv = T, tauhv = T;
         if (singles) {
-            tau.alloc(ctx, o, o, v, v); tauh.alloc(ctx, o, o, v, v);
-            tau_build(ctx, T.p, t.p, 1.0, tau.p(), o, v);
-            tau_build(ctx, T.p, t.p, 0.5, tauh.p(), o, v);
+            tau.alloc(ctx, o, o, v, v); tauh.alloc(ctx, o, o, v, v); Tp2.alloc(ctx, o, o, v, v);
+            amp_combos(ctx, T.p, t.p, Tt.p(), tau.p(), tauh.p(), Tp2.p(), o, v);
             tauv = tau; tauhv = tauh;
+        } else {
+            amp_combos(ctx, T.p, nullptr, Tt.p(), nullptr, nullptr, nullptr, o, v);
         }
         const Ten tau_S = last_slab(tauv, b0, vs), tauh_S = last_slab(tauhv, b0, vs);
         pcache.add(T, true); pcache.add(Tt, true);
@@ -348,12 +351,10 @@ struct CC {
         axpby(ctx, ns, -1.0, J_S.p, 0.0, WE.p());                                      // -<mb|je> = -(mj|eb)
         contract(ctx, 0.5, Vt, "mnef", T_S, "njfb", 1.0, WJ, "mejb");
         if (singles) {
-            DTen Tp2(ctx, o, o, v, v), Tph(ctx, o, o, v, v);
-            tau_build(ctx, T.p, t.p, 2.0, Tp2.p(), o, v);                             // T + 2 tt
-            axpby(ctx, n2, 0.5, T.p, 0.0, Tph.p());
-            tau_build(ctx, Tph.p(), t.p, 1.0, Tph.p(), o, v);                         // T/2 + tt
+            // T/2 + tt = (T + 2 tt) / 2: one operand serves both rings
+            pcache.add(Tp2, true);
             contract(ctx, -0.5, V, "mnef", last_slab(Tp2, b0, vs), "jnfb", 1.0, WJ, "mejb");
-            contract(ctx, 1.0, V, "nmef", last_slab(Tph, b0, vs), "jnfb", 1.0, WE, "mejb");
+            contract(ctx, 0.5, V, "nmef", last_slab(Tp2, b0, vs), "jnfb", 1.0, WE, "mejb");
             contract(ctx, 1.0, OA, "efmb", t, "jf", 1.0, WJ, "mejb");
             contract(ctx, -1.0, oovo, "mnej", tS, "nb", 1.0, WJ, "mejb");
             contract(ctx, -1.0, OA, "femb", t, "jf", 1.0, WE, "mejb");
@@ -367,12 +368,15 @@ struct CC {
         TraceTimer* tr_lad = new TraceTimer(ctx, "cc.part.ladders+H");
         DTen Lpp(ctx, o, o, v, vs), Lhh(ctx, o, o, v, vs), Hfull(ctx, o, o, v, v);
         const Ten H = last_slab(Hfull, b0, vs);
+        DBuf Tpm, Lpm;
         if (sa_ladder) {
             // tau.vvvv through the packed symmetric / antisymmetric parts: one batched GEMM of two
             // (o^2 x np)(np x nq) products, np = v(v+1)/2 summed pairs, nq = this rank's block of the
             // ~v^2/2 output pairs; the blocks of the other ranks are all-gathered (o^2 v^2 doubles in all)
+            // on the second stream, under the hole-hole ladder and the half residual below
             const int64_t oo = o * o, np = sa_pairs(v), nq_all = v * sa_slots(v);
-            DBuf Tpm(ctx, (size_t)(2 * oo * sa_ld)), Lpm(ctx, (size_t)(2 * oo * nq_all));
+            Tpm.alloc(ctx, (size_t)(2 * oo * sa_ld));
+            Lpm.alloc(ctx, (size_t)(2 * oo * nq_all));
             pack_tau_sa(ctx, tauv.p, oo, v, sa_ld, Tpm.p);
             GemmCall g;
             g.M = oo; g.N = sa_nq; g.K = np; g.batch = 2;
@@ -380,12 +384,16 @@ struct CC {
             g.B = Wsa.p(); g.ldb = sa_ld; g.strideB = sa_ld * sa_nq;
             g.C = Lpm.p + oo * sa_nq * ctx->rank; g.ldc = oo; g.strideC = oo * nq_all;
             dgemm(ctx, g);
-            {
+            if (ctx->nranks > 1) {
+                ensure_events();
+                JUES_CUDA(cudaEventRecord(ev_fork, ctx->stream));
+                StreamScope sc(ctx, ctx->comm_stream);
+                JUES_CUDA(cudaStreamWaitEvent(ctx->stream, ev_fork, 0));
                 TraceTimer tt(ctx, "cc.comm.gatherL");
                 all_gather_inplace(ctx, Lpm.p, (size_t)(oo * sa_nq));
                 all_gather_inplace(ctx, Lpm.p + oo * nq_all, (size_t)(oo * sa_nq));
+                JUES_CUDA(cudaEventRecord(ev_join, ctx->stream));
             }
-            unpack_ladder_sa(ctx, Lpm.p, oo, v, b0, vs, Lpp.p());
         } else {
             contract(ctx, 1.0, tauv, "ijef", W4, "efab", 0.0, Lpp, "ijab");
         }
@@ -409,6 +417,10 @@ struct CC {
             contract(ctx, -1.0, Q2, "imaj", tS, "mb", 1.0, H, "ijab");
             contract(ctx, 1.0, t, "ie", OB, "ajeb", 1.0, H, "ijab");     // t . <ab|ej>
             contract(ctx, -1.0, t, "ma", last_slab(ooov, b0, vs), "mjib", 1.0, H, "ijab");
+        }
+        if (sa_ladder) {
+            if (ctx->nranks > 1) JUES_CUDA(cudaStreamWaitEvent(ctx->stream, ev_join, 0));   // ladder blocks have arrived
+            unpack_ladder_sa(ctx, Lpm.p, o * o, v, b0, vs, Lpp.p());
         }
         delete tr_lad;
         { TraceTimer tt(ctx, "cc.comm.gatherH"); all_gather_inplace(ctx, Hfull.p(), ns); }
@@ -445,11 +457,51 @@ struct CC {
         use_graphs = sweeps >= 12 && fl < 1.5e12;     // < ~50 ms per sweep
     }
 
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;     // second-stream fork / join inside a sweep
+    void ensure_events() {
+        if (ev_fork) return;
+        JUES_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        JUES_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+
+    // Temporaries of a sweep (~300 stream-ordered allocations) come from one arena sized by the first sweep:
+    // no driver call per temporary, and a captured sweep contains kernels only.
+    Arena arena;
+    DBuf arena_block;
+    void install_arena(size_t need) {
+        if (ctx->arena || need == 0 || need > (size_t(24) << 30)) return;
+        const size_t bytes = ((need + need / 4 + (size_t(8) << 20)) + 255) & ~size_t(255);
+        try {
+            arena_block.alloc(ctx, bytes / 8);
+        } catch (const Error&) {
+            cudaGetLastError();
+            return;                               // no room: keep the stream-ordered pool
+        }
+        arena.reset(arena_block.p, bytes);
+        ctx->arena = &arena;
+    }
+
     void sweep() {
         static const bool no_graph = getenv("JUES_B200_NO_GRAPH") != nullptr;
+        static const bool no_arena = getenv("JUES_B200_NO_ARENA") != nullptr;
         const bool off = no_graph || ctx->trace > 0;
-        // the first sweep runs eagerly: it builds every lazily created operand copy / kernel attribute
-        if (off || !use_graphs || !graph_ok || ctx->nranks != 1 || eager_sweeps < 1) {
+        if (eager_sweeps < 1) {
+            // the first sweep runs eagerly from the pool: it builds every lazily created operand copy and
+            // kernel attribute, and measures what the temporaries of a sweep need
+            ctx->temp_live = ctx->temp_peak = 0;
+            ctx->measure = true;
+            try {
+                iterate();
+            } catch (...) {
+                ctx->measure = false;
+                throw;
+            }
+            ctx->measure = false;
+            ++eager_sweeps;
+            if (!no_arena) install_arena(ctx->temp_peak);
+            return;
+        }
+        if (off || !use_graphs || !graph_ok) {
             iterate();
             ++eager_sweeps;
             return;
@@ -460,6 +512,7 @@ struct CC {
             swap_amplitudes();              // what iterate() does on the host side
         } else {
             const Stats before = ctx->stats;
+            const long long big0 = ctx->big_allocs;
             cudaGraph_t graph = nullptr;
             bool captured = false;
             if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
@@ -470,7 +523,9 @@ struct CC {
                     threw = true;
                 }
                 const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-                if (!threw && e == cudaSuccess && graph &&
+                // a sweep that took blocks from the big-block cache is not replayed: the graph would keep
+                // using addresses that the cache may hand to somebody else
+                if (!threw && e == cudaSuccess && graph && ctx->big_allocs == big0 &&
                     cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess)
                     captured = true;
                 if (graph) cudaGraphDestroy(graph);
@@ -492,12 +547,16 @@ struct CC {
             g.delta.gemm_flops = ctx->stats.gemm_flops - before.gemm_flops;
             g.delta.gemm_launches = ctx->stats.gemm_launches - before.gemm_launches;
             g.delta.aux_launches = ctx->stats.aux_launches - before.aux_launches;
+            g.delta.collectives = ctx->stats.collectives - before.collectives;
+            g.delta.collective_bytes = ctx->stats.collective_bytes - before.collective_bytes;
             ctx->stats = before;
         }
         JUES_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
         ctx->stats.gemm_flops += g.delta.gemm_flops;
         ctx->stats.gemm_launches += g.delta.gemm_launches;
         ctx->stats.aux_launches += g.delta.aux_launches;
+        ctx->stats.collectives += g.delta.collectives;
+        ctx->stats.collective_bytes += g.delta.collective_bytes;
         ctx->stats.graph_launches += 1;
     }
 
@@ -770,10 +829,13 @@ MrccdResult mrccd_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, int maxit, doub
         double hbuf[8];
         {
             Timer t(ctx, "cc.iteration");
-            cc.iterate();                               // T2 = un-extrapolated new amplitudes, T2n = old ones
+            cc.sweep();                                 // T2 = un-extrapolated new amplitudes, T2n = old ones
             Pair p;
-            p.val.alloc(ctx, n2 / 2 + 1);
-            p.err.alloc(ctx, n2 / 2 + 1);
+            {
+                ArenaPause keep(ctx);                   // DIIS vectors live across sweeps
+                p.val.alloc(ctx, n2 / 2 + 1);
+                p.err.alloc(ctx, n2 / 2 + 1);
+            }
             to_float32(ctx, n2, cc.T2.p(), nullptr, reinterpret_cast<float*>(p.val.p));
             to_float32(ctx, n2, cc.T2.p(), cc.T2n.p(), reinterpret_cast<float*>(p.err.p));
             sqdiff_async(ctx, n2, cc.T2.p(), cc.T2n.p(), scal.p);          // ||T2new - T2old||^2 in FP64 (:205)

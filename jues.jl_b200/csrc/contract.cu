@@ -68,7 +68,15 @@ const double* permuted_operand(jues_ctx* ctx, const Ten& X, const char* ix, cons
             PermCache::Entry e;
             e.key = key;
             e.sweep = r.sweep;
-            e.buf.alloc(ctx, (size_t)X.size());
+            if (r.sweep) {
+                e.buf.alloc(ctx, (size_t)X.size());
+            } else {
+                // copies of static integrals live for the whole calculation: neither a temporary of the sweep
+                // that happens to build them nor a tenant of the sweep arena
+                MeasurePause mp(ctx);
+                ArenaPause ap(ctx);
+                e.buf.alloc(ctx, (size_t)X.size());
+            }
             t.p = e.buf.p;
             permute_axpby(ctx, 1.0, X, ix, 0.0, t, tgt.c_str());
             pc->entries.push_back(std::move(e));

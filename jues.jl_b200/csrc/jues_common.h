@@ -11,6 +11,8 @@
 #include <vector>
 #include <map>
 #include <set>
+#include <iterator>
+#include <algorithm>
 #include <stdexcept>
 #include <chrono>
 
@@ -68,6 +70,47 @@ struct Stats {
     void reset() { *this = Stats(); }
 };
 
+// One device block that serves the small stream-ordered temporaries of a sweep (~300 per sweep): a
+// host-side first-fit free list, no driver call per allocation.  All work of a context is on one stream, so
+// a block can be handed out again as soon as its owner released it.  Kernels captured into a CUDA graph
+// see arena addresses, which stay valid for as long as the arena lives (it outlives the graphs).
+struct Arena {
+    double* base = nullptr;
+    size_t bytes = 0;
+    std::map<size_t, size_t> free_by_off;   // offset -> length of free runs, coalesced on release
+    size_t live = 0, peak = 0;
+    bool has(const void* p) const {
+        return base && (const char*)p >= (const char*)base && (const char*)p < (const char*)base + bytes;
+    }
+    void reset(double* b, size_t n) {
+        base = b; bytes = n; free_by_off.clear(); live = peak = 0;
+        if (n) free_by_off[0] = n;
+    }
+    double* take(size_t n) {              // n: multiple of 256
+        for (auto it = free_by_off.begin(); it != free_by_off.end(); ++it) {
+            if (it->second < n) continue;
+            const size_t off = it->first, len = it->second;
+            free_by_off.erase(it);
+            if (len > n) free_by_off[off + n] = len - n;
+            live += n;
+            if (live > peak) peak = live;
+            return (double*)((char*)base + off);
+        }
+        return nullptr;
+    }
+    void give(const void* p, size_t n) {
+        size_t off = (size_t)((const char*)p - (const char*)base);
+        live -= n;
+        auto nx = free_by_off.lower_bound(off);
+        if (nx != free_by_off.end() && off + n == nx->first) { n += nx->second; nx = free_by_off.erase(nx); }
+        if (nx != free_by_off.begin()) {
+            auto pv = std::prev(nx);
+            if (pv->first + pv->second == off) { pv->second += n; return; }
+        }
+        free_by_off[off] = n;
+    }
+};
+
 }  // namespace jues
 
 // The opaque context of the C ABI.
@@ -93,6 +136,15 @@ struct jues_ctx {
     size_t big_cached_bytes = 0;
     double alloc_host_s = 0.0;   // host wall-clock spent inside device allocation calls (diagnostic)
     long long alloc_calls = 0;
+    // small (pool-sized) allocations: live / peak bytes since the last reset (sizes the sweep arena), and the
+    // arena itself while a coupled-cluster driver has one installed
+    size_t small_live = 0, small_peak = 0;
+    // every allocation made while `measure` is on (the first sweep), except those made under MeasurePause
+    // (operand copies that persist for the whole calculation): what a sweep's temporaries need at once
+    bool measure = false;
+    size_t temp_live = 0, temp_peak = 0;
+    long long big_allocs = 0;     // allocations of big_bytes or more NOT served by the arena (a sweep that makes any is not captured)
+    jues::Arena* arena = nullptr;
     // multi-GPU (one process per GPU): rank / world size and an NCCL communicator (opaque here)
     int rank = 0;
     int nranks = 1;
@@ -142,8 +194,8 @@ struct DBuf {
     DBuf& operator=(DBuf&& o) noexcept {
         if (this != &o) {
             release();
-            ctx = o.ctx; p = o.p; n = o.n; cap = o.cap; from_big = o.from_big;
-            o.p = nullptr; o.n = 0; o.cap = 0; o.from_big = false;
+            ctx = o.ctx; p = o.p; n = o.n; cap = o.cap; from_big = o.from_big; from_arena = o.from_arena; counted = o.counted;
+            o.p = nullptr; o.n = 0; o.cap = 0; o.from_big = false; o.from_arena = false; o.counted = false;
         }
         return *this;
     }
@@ -156,6 +208,8 @@ struct DBuf {
     static constexpr size_t kBigBytes = size_t(64) << 20;
     size_t cap = 0;  // bytes actually held (big blocks may be slightly larger than requested)
     bool from_big = false;   // block came from cudaMalloc / the context's big-block cache
+    bool from_arena = false; // block came from the context's sweep arena
+    bool counted = false;    // included in ctx->temp_live
     void alloc(jues_ctx* c, size_t n_) {
         release();
         ctx = c;
@@ -168,7 +222,25 @@ struct DBuf {
         cudaError_t e = cudaSuccess;
         cap = bytes;
         from_big = bytes >= c->big_bytes;
+        from_arena = false;
+        counted = c->measure;
+        if (counted) {
+            c->temp_live += bytes;
+            if (c->temp_live > c->temp_peak) c->temp_peak = c->temp_live;
+        }
+        if (c->arena) {
+            p = c->arena->take(bytes);
+            if (p) {
+                from_arena = true;
+                from_big = false;
+                c->alloc_calls++;
+                c->bytes_allocated += cap;
+                if (c->bytes_allocated > c->bytes_peak) c->bytes_peak = c->bytes_allocated;
+                return;
+            }
+        }
         if (from_big) {
+            c->big_allocs++;
             auto it = c->big_free.lower_bound(bytes);
             if (it != c->big_free.end() && it->first <= bytes + bytes / 8) {
                 p = it->second;
@@ -200,20 +272,29 @@ struct DBuf {
         }
         c->bytes_allocated += cap;
         if (c->bytes_allocated > c->bytes_peak) c->bytes_peak = c->bytes_allocated;
+        if (!from_big) {
+            c->small_live += cap;
+            if (c->small_live > c->small_peak) c->small_peak = c->small_live;
+        }
     }
     void release() {
         if (p) {
-            if (from_big) {
+            if (counted) { ctx->temp_live -= std::min(ctx->temp_live, cap); counted = false; }
+            if (from_arena) {
+                if (ctx->arena && ctx->arena->has(p)) ctx->arena->give(p, cap);   // else: the arena is gone with its block
+            } else if (from_big) {
                 ctx->big_free.emplace(cap, p);
                 ctx->big_cached_bytes += cap;
             } else {
                 cudaFreeAsync(p, ctx->stream);
+                ctx->small_live -= cap;
             }
             ctx->bytes_allocated -= cap;
             p = nullptr;
             n = 0;
             cap = 0;
             from_big = false;
+            from_arena = false;
         }
     }
     void zero() { JUES_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), ctx->stream)); }
@@ -273,6 +354,22 @@ struct StreamScope {
     cudaStream_t saved;
     StreamScope(jues_ctx* c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
     ~StreamScope() { ctx->stream = saved; }
+};
+
+// Allocations that persist beyond the sweep being measured do not count as its temporaries.
+struct MeasurePause {
+    jues_ctx* ctx;
+    bool saved;
+    explicit MeasurePause(jues_ctx* c) : ctx(c), saved(c->measure) { c->measure = false; }
+    ~MeasurePause() { ctx->measure = saved; }
+};
+
+// Allocations that outlive a sweep must not come from the sweep arena.
+struct ArenaPause {
+    jues_ctx* ctx;
+    Arena* saved;
+    explicit ArenaPause(jues_ctx* c) : ctx(c), saved(c->arena) { c->arena = nullptr; }
+    ~ArenaPause() { ctx->arena = saved; }
 };
 
 // JUES_B200_TRACE=1: fine-grained CUDA-event timings

@@ -20,7 +20,6 @@
 //     (block tree -> one slot per batch; the slots are summed in a fixed order at the end).
 // Flops: 6 * 2 v^3 (v + o) per triple, o(o+1)(o+2)/6 triples -- the same count as the reference.
 #include "pt.h"
-#include "pt_fused.h"
 #include "dgemm.h"
 #include "dist.h"
 
@@ -28,12 +27,6 @@
 
 namespace jues {
 
-// fused assemble + energy kernel (48 v^3 instead of 80 v^3 bytes per triple); JUES_B200_PT_FUSED=0 selects the
-// two-kernel path
-static bool pt_use_fused() {
-    const char* e = getenv("JUES_B200_PT_FUSED");
-    return e ? atoi(e) != 0 : false;
-}
 
 namespace {
 
@@ -124,23 +117,6 @@ __global__ void pt_energy_kernel(const double* __restrict__ W, const double* __r
     if (threadIdx.x == 0) partial[blockIdx.x] = r;
 }
 
-// Experimental (JUES_B200_PT_FUSED=1): assemble + energy in one pass.  Work items are (kk, pair b >= c);
-// the threads of a block walk a = b .. v-1 and evaluate pt_triple_energy straight from the six X
-// families (36 + 18 loads per triple, no W / V arrays: 48 v^3 instead of 80 v^3 bytes per occupied
-// triple, and no thread is launched for the 5/6 of the index cube outside a >= b >= c).  The index
-// function is shared with a host build that the CPU test-suite checks (tests/test_pt_fused_host.py).
-__global__ void pt_fused_kernel(PtFusedArgs g, double* __restrict__ partial) {
-    const long long nbc = (long long)g.v * (g.v + 1) / 2, items = nbc * g.kb;
-    double acc = 0.0;
-    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-        const int kk = (int)(it / nbc);
-        int b, c;
-        pt_pair_decode(it % nbc, &b, &c);
-        for (int a = b + (int)threadIdx.x; a < g.v; a += (int)blockDim.x) acc += pt_triple_energy(g, kk, a, b, c);
-    }
-    const double r = block_sum<128>(acc);
-    if (threadIdx.x == 0) partial[blockIdx.x] = r;
-}
 
 __global__ void pt_slot_reduce_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
     double acc = 0.0;
@@ -231,7 +207,6 @@ double pt_dev(jues_ctx* ctx, const PtInputs& in, double* scratch, size_t scratch
     DBuf slots(ctx, (size_t)nslots + 1);
     slots.zero();
     int64_t slot = 0, pair = 0;
-    const bool fused = pt_use_fused();
     for (int64_t i = 0; i < nocc; ++i) {
         for (int64_t j = 0; j <= i; ++j, ++pair) {
             if (pair % ctx->nranks != ctx->rank) continue;
@@ -247,19 +222,6 @@ double pt_dev(jues_ctx* ctx, const PtInputs& in, double* scratch, size_t scratch
                 x_blocks(ctx, in, j, 0, i, 0, k0, 1, kb, X.p + 5 * fam);   // X(j,i,k)
                 delete tg;
                 TraceTimer ta(ctx, "pt.assemble+energy");
-                if (fused) {
-                    PtFusedArgs fa{X.p, in.Vv, in.t1, in.eo, in.ev, (int)o, (int)v, (int)i, (int)j, (int)k0, (int)kb};
-                    const long long items = v * (v + 1) / 2 * kb;
-                    const int fgrid = (int)std::min<long long>(std::min<long long>(items, (long long)ctx->sm_count * 32),
-                                                               (long long)ctx->red_cap - 4);
-                    pt_fused_kernel<<<fgrid, 128, 0, ctx->stream>>>(fa, ctx->red_dev);
-                    JUES_CUDA(cudaGetLastError());
-                    pt_slot_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, fgrid, slots.p + slot);
-                    JUES_CUDA(cudaGetLastError());
-                    ctx->stats.aux_launches += 2;
-                    ++slot;
-                    continue;
-                }
                 const int grid = ew_grid(ctx, (size_t)fam, 256);
                 pt_assemble_kernel<<<grid, 256, 0, ctx->stream>>>(X.p, in.Vv, in.t1, W.p, V.p, (int)o, (int)v,
                                                                   (int)i, (int)j, (int)k0, (int)kb);

@@ -172,6 +172,37 @@ __global__ void tau_kernel(const double* __restrict__ T, const double* __restric
     }
 }
 
+// All amplitude-derived operands of a sweep in ONE pass over T2 (one block per (a,b): the o x o block holds
+// both T[i,j] and T[j,i]):  Tt = 2T - T(ji),  tau = T + t(x)t,  tauh = T + 1/2 t(x)t,  Tp2 = T + 2 t(x)t.
+// Reads 8 B, writes 8 B per output element; the five separate kernels it replaces moved 2.5x as much.
+__global__ void amp_combos_kernel(const double* __restrict__ T, const double* __restrict__ t1,
+                                  double* __restrict__ Tt, double* __restrict__ tau, double* __restrict__ tauh,
+                                  double* __restrict__ Tp2, int o, int v) {
+    extern __shared__ double sh[];  // o x (o+1)
+    const long long oo = (long long)o * o;
+    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
+        const int a = (int)(ab % v), b = (int)(ab / v);
+        const long long base = ab * oo;
+        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+            const int i = e % o, j = e / o;
+            sh[j * (o + 1) + i] = T[base + e];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
+            const int i = e % o, j = e / o;
+            const double x = sh[j * (o + 1) + i], xt = sh[i * (o + 1) + j];
+            Tt[base + e] = 2.0 * x - xt;
+            if (t1) {
+                const double tt = t1[i + (long long)o * a] * t1[j + (long long)o * b];
+                tau[base + e] = x + tt;
+                tauh[base + e] = x + 0.5 * tt;
+                Tp2[base + e] = x + 2.0 * tt;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void divide_Dijab_kernel(const double* __restrict__ R, double* __restrict__ Tn,
                                     const double* __restrict__ eo, const double* __restrict__ ev, int o,
                                     int v) {
@@ -597,6 +628,20 @@ void splitk_reduce(jues_ctx* ctx, const double* W, int nsplit, int64_t M, int64_
 void tau_build(jues_ctx* ctx, const double* T, const double* t1, double c, double* out, int64_t o, int64_t v) {
     const size_t total = (size_t)o * o * v * v;
     tau_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(T, t1, c, out, (int)o, (int)v);
+    AUX_LAUNCHED(ctx);
+}
+
+void amp_combos(jues_ctx* ctx, const double* T, const double* t1, double* Tt, double* tau, double* tauh,
+                double* Tp2, int64_t o, int64_t v) {
+    const size_t smem = (size_t)o * (o + 1) * sizeof(double);
+    JUES_REQUIRE(smem <= 200 * 1024, "amp_combos: nocc too large for the shared-memory block");
+    if (ctx->smem_attr_done.insert((const void*)amp_combos_kernel).second)
+        JUES_CUDA(cudaFuncSetAttribute(amp_combos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long blocks = (long long)v * v;
+    const long long cap = (long long)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) return;
+    amp_combos_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(T, t1, Tt, tau, tauh, Tp2, (int)o, (int)v);
     AUX_LAUNCHED(ctx);
 }
 

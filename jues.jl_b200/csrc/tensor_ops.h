@@ -65,6 +65,11 @@ void splitk_reduce(jues_ctx* ctx, const double* W, int nsplit, int64_t M, int64_
 // out[i,j,a,b] = T[i,j,a,b] + c * t[i,a] * t[j,b]        (o,o,v,v), t is (o,v); T may be null (=0)
 void tau_build(jues_ctx* ctx, const double* T, const double* t1, double c, double* out, int64_t o, int64_t v);
 
+// One pass over T2 (o,o,v,v): Tt = 2T - T(ji); with t1 (o,v) also tau = T + t(x)t, tauh = T + 1/2 t(x)t,
+// Tp2 = T + 2 t(x)t  (t1 == nullptr: only Tt is written, the other outputs may be null)
+void amp_combos(jues_ctx* ctx, const double* T, const double* t1, double* Tt, double* tau, double* tauh,
+                double* Tp2, int64_t o, int64_t v);
+
 // Tnew[i,j,a,b] = R[i,j,a,b] / (eo[i] + eo[j] - ev[a] - ev[b])       (may be in place)
 void divide_Dijab(jues_ctx* ctx, const double* R, double* Tnew, const double* eo, const double* ev,
                   int64_t o, int64_t v);

@@ -270,19 +270,3 @@ def test_mrccd_diis(ctx, N, o, seed):
     e, T2 = jb.mRCCD.do_rccd(w, ctx=ctx, return_T2=True)
     assert e == got["ecc"] and np.array_equal(T2, got["T2"])           # deterministic
     assert jb.mRCCD.do_rccd(w, ctx=ctx, maxit=2, _return_all=True)["iterations"] == 2
-
-
-# ------------------------------------------------------------------------------------------
-# experimental code paths (off by default; not part of the product path until measured)
-# ------------------------------------------------------------------------------------------
-@pytest.mark.skipif(os.environ.get("JUES_B200_TEST_EXPERIMENTAL") is None,
-                    reason="experimental kernels are validated explicitly (JUES_B200_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("N,o,seed", [(8, 3, 7), (12, 5, 13), (20, 6, 4)])
-def test_compute_pT_fused_kernel(ctx, N, o, seed, monkeypatch):
-    """JUES_B200_PT_FUSED=1: assemble + energy of the (T) in one kernel (pt.cu: pt_fused_kernel)."""
-    kw = pt_inputs(N, o, seed)
-    ref = oa.compute_pT(**kw)
-    plain = jb.compute_pT(ctx=ctx, **kw)
-    monkeypatch.setenv("JUES_B200_PT_FUSED", "1")
-    fused = jb.compute_pT(ctx=ctx, **kw)
-    assert abs(fused - ref) <= E_TOL and abs(fused - plain) <= 1e-12

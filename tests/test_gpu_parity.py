@@ -318,3 +318,90 @@ def test_gemm_repeatable(ctx):
                                  ("N", "N", 124, 124, 144, 300), ("T", "N", 700, 700, 700, 1)]:
         nb, w = ctx.gemm_stress(tA, tB, M, N, K, b, reps=5)
         assert nb == 0 and w == 0.0, (tA, tB, M, N, K, b, nb, w)
+
+
+# ---- parity at the BASELINE shapes --------------------------------------------------------------------
+def test_c3_against_committed_oracle_trace(ctx):
+    """BASELINE config 3 (nbf=120, nocc=20), the bench workload: every one of the 40 sweeps against the
+    committed trace of the literal oracle (tests/golden/make_bench_golden.py): energy, ||T1||, ||T2|| per
+    sweep and 64 sampled elements of the final T2."""
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_ehist_nbf120_nocc20.npz")
+    gold = np.load(p)
+    nbf, nocc = int(gold["nbf"]), int(gold["nocc"])
+    Cao, Cav, eps = jb.synth.orbitals(nbf, nocc, int(gold["seed"]))
+    g = jb.DeviceFourTensor.synth_eri(nbf, seed=int(gold["seed"]), scale=jb.synth.counter_scale(nbf), ctx=ctx)
+    w = jb.Wfn(nocc, nbf - nocc, eps, Cao, Cav, g)
+    rec = []
+    ctx.set_amplitude_callback(lambda it, e, T1, T2: rec.append((e, float(np.linalg.norm(T1)), float(np.linalg.norm(T2)),
+                                                                  T2 if it == 40 else None, T1 if it == 40 else None)))
+    try:
+        e = jb.RCCSD.do_rccsd(w, ctx=ctx)
+    finally:
+        ctx.set_amplitude_callback(None)
+        g.free()
+    assert len(rec) == 41
+    assert np.abs(np.array([r[0] for r in rec]) - gold["e_hist"]).max() <= E_TOL
+    assert abs(e - gold["e_hist"][40]) <= E_TOL
+    # norms of ~6e6 amplitudes: 1e-9 per element bounds the norm difference by 1e-9 * sqrt(n)
+    assert np.abs(np.array([r[1] for r in rec]) - gold["t1_norm"]).max() <= AMP_TOL * np.sqrt(nocc * (nbf - nocc))
+    assert np.abs(np.array([r[2] for r in rec]) - gold["t2_norm"]).max() <= AMP_TOL * nocc * (nbf - nocc)
+    T2, T1 = rec[40][3], rec[40][4]
+    idx = gold["t2_idx"]
+    assert np.abs(T2[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]] - gold["t2_samples"]).max() <= AMP_TOL
+    assert np.abs(T1 - gold["T1"]).max() <= AMP_TOL
+
+
+def test_block_streamed_paths_at_n72(ctx):
+    """The sub-block pipeline of the one-pass transform above toy sizes (nbf=72, several sub-blocks forced):
+    host array, dense device tensor and the storage-less generated tensor give the same RMP2 energy as the
+    oracle and the same RCCSD energies as each other."""
+    import os
+    N, o = 72, 10
+    sc = jb.synth.counter_scale(N)
+    Cao, Cav, eps = jb.synth.orbitals(N, o, 9)
+    gh = jb.synth.counter_eri(N, 9, sc)
+    wo = orc.Wfn(o, N - o, eps, Cao, Cav, gh)
+    e_ref = orc.do_rmp2(wo)
+    gd = jb.DeviceFourTensor.synth_eri(N, seed=9, scale=sc, ctx=ctx)
+    gv = jb.DeviceFourTensor.synth_eri(N, seed=9, scale=sc, ctx=ctx, virtual=True)
+    os.environ["JUES_B200_FORCE_STREAM"] = "1"
+    try:
+        res = {}
+        for name, g in (("host", gh), ("dense", gd), ("virtual", gv)):
+            w = jb.Wfn(o, N - o, eps, Cao, Cav, g)
+            h = []
+            res[name] = (jb.do_rmp2(w, ctx=ctx), jb.RCCSD.do_rccsd(w, ctx=ctx, _maxit=3, _e_hist=h), h)
+    finally:
+        del os.environ["JUES_B200_FORCE_STREAM"]
+        gd.free(); gv.free()
+    for name, (e2, ecc, h) in res.items():
+        assert abs(e2 - e_ref) <= E_TOL, (name, e2, e_ref)
+        assert np.abs(np.array(h) - np.array(res["host"][2])).max() <= 1e-12, name
+
+
+def test_sampled_elements_of_a_large_generated_transform(ctx):
+    """SURVEY 8d parity protocol for shapes the oracle cannot transform: <ij|ab> of the storage-less generated
+    AO tensor at nbf=128 (2.7e8 AO elements never held anywhere), sampled (i, j) pairs checked against host
+    quarter transforms of synth.counter_eri_element."""
+    N, o = 128, 6
+    v = N - o
+    sc = jb.synth.counter_scale(N)
+    Cao, Cav, eps = jb.synth.orbitals(N, o, 3)
+    gv = jb.DeviceFourTensor.synth_eri(N, seed=3, scale=sc, ctx=ctx, virtual=True)
+    try:
+        w = jb.Wfn(o, v, eps, Cao, Cav, gv)
+        ijab = jb.get_eri(w, "OOVV", ctx=ctx)
+        ijab = ijab.to_array() if hasattr(ijab, "to_array") else np.asarray(ijab)
+    finally:
+        gv.free()
+    pairs = [(0, 0), (2, 5), (5, 1)]
+    # h[nu, sig] = sum_{mu lam} C[mu,i] C[lam,j] g[mu,nu,lam,sig], one sigma plane at a time
+    h = np.zeros((len(pairs), N, N))
+    for s_ in range(N):
+        plane = jb.synth.counter_eri(N, 3, sc, sig_range=(s_, s_ + 1))[:, :, :, 0]
+        for k, (i, j) in enumerate(pairs):
+            h[k, :, s_] = np.einsum("m,mnl,l->n", Cao[:, i], plane, Cao[:, j], optimize=True)
+    for k, (i, j) in enumerate(pairs):
+        ref = Cav.T @ h[k] @ Cav                               # <ij|ab> = (ia|jb)
+        assert np.abs(ijab[i, j] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) + 1e-13, (i, j)
