@@ -53,6 +53,15 @@ const char* jues_b200_version(void);
  * torch.distributed / MPI / a file).  Collectives used on the path: all-gather of the new T2
  * slab and all-reduce of energy partials.  The reference's only
  * multi-process design is ParCCD.jl:23-86,241-295 (Julia Distributed, slabs over virtual b).  */
+/* Multi-GPU inside ONE process (what `Input.exec` / `com(JuWfn; ...)` needs, Input.jl:58-71: the reference's
+ * entry points are called once, from one task): contexts on devices 0..ngpu-1 (ngpu <= 0: every visible
+ * device), one NCCL communicator per device (ncclCommInitAll), returned as ONE handle -- the leader.  Every
+ * entry point below that shards (rmp2, rccd, rccsd, auto_rccsd, mrccd and their _t4 forms with a generated
+ * tensor) called on the leader runs on all devices, one host thread per GPU, and returns the leader's
+ * results; the others run on the leader's GPU alone.  jues_b200_finalize(leader) releases everything.   */
+int jues_b200_init_multi(jues_ctx** leader, int ngpu);
+int jues_b200_group_size(jues_ctx* ctx);   /* devices behind this handle (1 for a plain context) */
+
 int jues_b200_nccl_unique_id(unsigned char id_out[128]);
 int jues_b200_init_dist(jues_ctx* ctx, int rank, int nranks, const unsigned char id[128]);
 

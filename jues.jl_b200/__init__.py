@@ -128,6 +128,22 @@ class Context:
         self.device = device
         self._cb_keep = None
 
+    @classmethod
+    def multi(cls, ngpu: int = 0) -> "Context":
+        """Single-process multi-GPU: one handle in front of `ngpu` devices (0 = every visible one); the
+        sharding entry points called with it run on all of them (jues_b200_init_multi)."""
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.jues_b200_init_multi(C.byref(h), int(ngpu))
+        if rc != 0:
+            raise JuesError(rc, self._lib.jues_b200_last_error(None).decode())
+        self._h = h
+        self.device = 0
+        self._cb_keep = None
+        self.nranks = self._lib.jues_b200_group_size(h)
+        return self
+
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc: int):
         if rc != 0:

@@ -96,6 +96,8 @@ SIGNATURES = {
                                      c_double_p, c_double_p]),
     "jues_b200_sa_ladder": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int,
                                       c_double_p]),
+    "jues_b200_init_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "jues_b200_group_size": (C.c_int, [C.c_void_p]),
     "jues_b200_set_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "jues_b200_get_phases": (C.c_int, [C.c_void_p, C.POINTER(Phase), C.c_int]),
     "jues_b200_get_counters": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_int64_p, c_int64_p]),

@@ -259,6 +259,11 @@ extern "C" int jues_b200_transform_stress(jues_ctx* ctx, const jues_t4* gao, con
 // ---------------------------------------------------------------------------------------------
 extern "C" int jues_b200_rmp2(jues_ctx* ctx, const double* gao, int64_t nao, const double* Cao, int64_t nocc,
                               const double* Cav, int64_t nvir, const double* eps, double* e_mp2) {
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            return jues_b200_rmp2(m, gao, nao, Cao, nocc, Cav, nvir, eps, lead ? e_mp2 : &e_);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     JUES_REQUIRE(e_mp2 != nullptr, "null output");
@@ -273,6 +278,15 @@ extern "C" int jues_b200_rmp2(jues_ctx* ctx, const double* gao, int64_t nao, con
 
 extern "C" int jues_b200_rmp2_t4(jues_ctx* ctx, const jues_t4* gao, const double* Cao, int64_t nocc,
                                  const double* Cav, int64_t nvir, const double* eps, double* e_mp2) {
+    if (is_group_call(ctx) && gao && !gao->virtual_synth) {
+        ctx->last_error = "a dense device tensor lives on one GPU: pass the host array or a generated tensor to a multi-GPU group";
+        return JUES_B200_ESTATE;
+    }
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            return jues_b200_rmp2_t4(m, gao, Cao, nocc, Cav, nvir, eps, lead ? e_mp2 : &e_);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     check_t4_is_gao(gao);
@@ -308,6 +322,12 @@ void run_cc(jues_ctx* ctx, GaoSource& src, const double* Cao, int64_t nocc, cons
 extern "C" int jues_b200_rccd(jues_ctx* ctx, const double* gao, int64_t nao, const double* Cao, int64_t nocc,
                               const double* Cav, int64_t nvir, const double* eps, int maxit, int guess_mode,
                               double* e_ccd, double* e_hist, double* T2_out) {
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            return jues_b200_rccd(m, gao, nao, Cao, nocc, Cav, nvir, eps, maxit, guess_mode, lead ? e_ccd : &e_,
+                                  lead ? e_hist : nullptr, lead ? T2_out : nullptr);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     JUES_REQUIRE(guess_mode == 0 || guess_mode == 1, "guess_mode must be 0 (reference) or 1 (MP2)");
@@ -321,6 +341,16 @@ extern "C" int jues_b200_rccd(jues_ctx* ctx, const double* gao, int64_t nao, con
 extern "C" int jues_b200_rccd_t4(jues_ctx* ctx, const jues_t4* gao, const double* Cao, int64_t nocc,
                                  const double* Cav, int64_t nvir, const double* eps, int maxit,
                                  int guess_mode, double* e_ccd, double* e_hist, double* T2_out) {
+    if (is_group_call(ctx) && gao && !gao->virtual_synth) {
+        ctx->last_error = "a dense device tensor lives on one GPU: pass the host array or a generated tensor to a multi-GPU group";
+        return JUES_B200_ESTATE;
+    }
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            return jues_b200_rccd_t4(m, gao, Cao, nocc, Cav, nvir, eps, maxit, guess_mode, lead ? e_ccd : &e_,
+                                     lead ? e_hist : nullptr, lead ? T2_out : nullptr);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     check_t4_is_gao(gao);
@@ -335,6 +365,12 @@ extern "C" int jues_b200_rccd_t4(jues_ctx* ctx, const jues_t4* gao, const double
 extern "C" int jues_b200_rccsd(jues_ctx* ctx, const double* gao, int64_t nao, const double* Cao, int64_t nocc,
                                const double* Cav, int64_t nvir, const double* eps, int maxit, double* e_ccsd,
                                double* e_hist, double* T1_out, double* T2_out) {
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            return jues_b200_rccsd(m, gao, nao, Cao, nocc, Cav, nvir, eps, maxit, lead ? e_ccsd : &e_,
+                                   lead ? e_hist : nullptr, lead ? T1_out : nullptr, lead ? T2_out : nullptr);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     Timer total(ctx, "total");
@@ -347,6 +383,16 @@ extern "C" int jues_b200_rccsd(jues_ctx* ctx, const double* gao, int64_t nao, co
 extern "C" int jues_b200_rccsd_t4(jues_ctx* ctx, const jues_t4* gao, const double* Cao, int64_t nocc,
                                   const double* Cav, int64_t nvir, const double* eps, int maxit,
                                   double* e_ccsd, double* e_hist, double* T1_out, double* T2_out) {
+    if (is_group_call(ctx) && gao && !gao->virtual_synth) {
+        ctx->last_error = "a dense device tensor lives on one GPU: pass the host array or a generated tensor to a multi-GPU group";
+        return JUES_B200_ESTATE;
+    }
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            return jues_b200_rccsd_t4(m, gao, Cao, nocc, Cav, nvir, eps, maxit, lead ? e_ccsd : &e_,
+                                      lead ? e_hist : nullptr, lead ? T1_out : nullptr, lead ? T2_out : nullptr);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     check_t4_is_gao(gao);
@@ -604,6 +650,14 @@ extern "C" int jues_b200_auto_rccsd(jues_ctx* ctx, const double* gao, int64_t na
                                     const jues_b200_cc_options* opt, double* e_cc, double* e_pt,
                                     int* iterations, int* converged, double* e_hist, double* rms_hist,
                                     double* T1_out, double* T2_out) {
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_, p_;
+            int i_, c_;
+            return jues_b200_auto_rccsd(m, gao, nao, hao, Ca, nmo, ndocc, opt, lead ? e_cc : &e_, lead ? e_pt : &p_,
+                                        lead ? iterations : &i_, lead ? converged : &c_, lead ? e_hist : nullptr,
+                                        lead ? rms_hist : nullptr, lead ? T1_out : nullptr, lead ? T2_out : nullptr);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     Timer total(ctx, "total");
@@ -618,6 +672,18 @@ extern "C" int jues_b200_auto_rccsd_t4(jues_ctx* ctx, const jues_t4* gao, const 
                                        int64_t nmo, int64_t ndocc, const jues_b200_cc_options* opt,
                                        double* e_cc, double* e_pt, int* iterations, int* converged,
                                        double* e_hist, double* rms_hist, double* T1_out, double* T2_out) {
+    if (is_group_call(ctx) && gao && !gao->virtual_synth) {
+        ctx->last_error = "a dense device tensor lives on one GPU: pass the host array or a generated tensor to a multi-GPU group";
+        return JUES_B200_ESTATE;
+    }
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_, p_;
+            int i_, c_;
+            return jues_b200_auto_rccsd_t4(m, gao, hao, Ca, nmo, ndocc, opt, lead ? e_cc : &e_, lead ? e_pt : &p_,
+                                           lead ? iterations : &i_, lead ? converged : &c_, lead ? e_hist : nullptr,
+                                           lead ? rms_hist : nullptr, lead ? T1_out : nullptr, lead ? T2_out : nullptr);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     check_t4_is_gao(gao);
@@ -712,6 +778,14 @@ void run_mrccd(jues_ctx* ctx, GaoSource& src, const double* Cao, int64_t nocc, c
 extern "C" int jues_b200_mrccd(jues_ctx* ctx, const double* gao, int64_t nao, const double* Cao, int64_t nocc,
                                const double* Cav, int64_t nvir, const double* eps, int maxit, double* e_ccd,
                                int* iterations, double* rms_hist, double* e_hist, double* T2_out) {
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            int i_;
+            return jues_b200_mrccd(m, gao, nao, Cao, nocc, Cav, nvir, eps, maxit, lead ? e_ccd : &e_,
+                                   lead ? iterations : &i_, lead ? rms_hist : nullptr, lead ? e_hist : nullptr,
+                                   lead ? T2_out : nullptr);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     Timer total(ctx, "total");
@@ -724,6 +798,18 @@ extern "C" int jues_b200_mrccd(jues_ctx* ctx, const double* gao, int64_t nao, co
 extern "C" int jues_b200_mrccd_t4(jues_ctx* ctx, const jues_t4* gao, const double* Cao, int64_t nocc,
                                   const double* Cav, int64_t nvir, const double* eps, int maxit, double* e_ccd,
                                   int* iterations, double* rms_hist, double* e_hist, double* T2_out) {
+    if (is_group_call(ctx) && gao && !gao->virtual_synth) {
+        ctx->last_error = "a dense device tensor lives on one GPU: pass the host array or a generated tensor to a multi-GPU group";
+        return JUES_B200_ESTATE;
+    }
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            int i_;
+            return jues_b200_mrccd_t4(m, gao, Cao, nocc, Cav, nvir, eps, maxit, lead ? e_ccd : &e_,
+                                      lead ? iterations : &i_, lead ? rms_hist : nullptr, lead ? e_hist : nullptr,
+                                      lead ? T2_out : nullptr);
+        });
     JUES_API_BEGIN(ctx)
     begin_call(ctx);
     check_t4_is_gao(gao);

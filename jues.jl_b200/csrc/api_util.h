@@ -6,6 +6,19 @@ namespace jues {
 
 extern std::string g_init_error;
 
+// An entry point that does not fan out over a single-process multi-GPU group runs on the leader alone:
+// for its duration the leader is a one-rank context (no collective may wait for members that are not there).
+struct SoloGuard {
+    jues_ctx* ctx;
+    int nranks, rank;
+    bool active;
+    explicit SoloGuard(jues_ctx* c) : ctx(c), nranks(c->nranks), rank(c->rank),
+                                      active(c->group != nullptr && !c->in_group_call) {
+        if (active) { ctx->nranks = 1; ctx->rank = 0; }
+    }
+    ~SoloGuard() { if (active) { ctx->nranks = nranks; ctx->rank = rank; } }
+};
+
 // exception -> status code conversion at the ABI boundary
 #define JUES_API_BEGIN(ctx)                                   \
     if (!(ctx)) return JUES_B200_EINVAL;                      \
@@ -14,7 +27,8 @@ extern std::string g_init_error;
         if (sd__ != cudaSuccess) {                            \
             (ctx)->last_error = cudaGetErrorString(sd__);     \
             return JUES_B200_ECUDA;                           \
-        }
+        }                                                     \
+        ::jues::SoloGuard solo__(ctx);
 
 #define JUES_API_END(ctx)                                     \
         return JUES_B200_OK;                                  \

@@ -470,7 +470,8 @@ struct CC {
     DBuf arena_block;
     void install_arena(size_t need) {
         if (ctx->arena || need == 0 || need > (size_t(24) << 30)) return;
-        const size_t bytes = ((need + need / 4 + (size_t(8) << 20)) + 255) & ~size_t(255);
+        // first-fit over blocks of very different sizes fragments: half as much again as the first sweep held
+        const size_t bytes = ((need + need / 2 + (size_t(16) << 20)) + 255) & ~size_t(255);
         try {
             arena_block.alloc(ctx, bytes / 8);
         } catch (const Error&) {
@@ -683,6 +684,8 @@ CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int max
     JUES_CUDA(cudaStreamSynchronize(ctx->stream));
     res.energy = res.e_hist[maxit];
     ctx->timings.emplace_back("cc.graph_launches", (float)ctx->stats.graph_launches);
+    ctx->timings.emplace_back("cc.arena_mb", (float)(cc.arena.bytes / 1048576.0));
+    ctx->timings.emplace_back("cc.arena_misses", (float)cc.arena.misses);
     cc.download(singles ? T1_out : nullptr, T2_out);
     return res;
 }

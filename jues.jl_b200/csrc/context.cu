@@ -76,6 +76,13 @@ extern "C" int jues_b200_init(jues_ctx** out, int device) {
 
 extern "C" void jues_b200_finalize(jues_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->group) {                       // leader of a single-process multi-GPU group: members first
+        std::vector<jues_ctx*>* g = ctx->group;
+        ctx->group = nullptr;
+        for (jues_ctx* m : *g)
+            if (m != ctx) jues_b200_finalize(m);
+        delete g;
+    }
     cudaSetDevice(ctx->device);
     resolve_timers(ctx);
     jues::dist_teardown(ctx);

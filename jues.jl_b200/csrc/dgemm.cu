@@ -78,32 +78,12 @@ void make_map(jues_ctx* ctx, CUtensorMap* map, const double* base, int64_t d0, i
     }
 }
 
-// DMMA issue load (8x8 accumulator tiles per k-quad) of the busiest of the four schedulers of an SM for a
-// tile that holds mr x nc elements of C.  The small tile configurations skip 8x8 sub-tiles that lie entirely
-// beyond M or N (dgemm_sm100.cuh), so a ragged or skinny tile costs what it holds, not what it spans.
-int smsp_load(const Cfg& c, int64_t mr, int64_t nc) {
-    const int warpsM = c.BM / c.WM, warpsN = c.BN / c.WN, TI = c.WM / 8, TJ = c.WN / 8;
-    const bool skip = c.BM * c.BN <= 8192;
-    int load[4] = {0, 0, 0, 0};
-    for (int w = 0; w < warpsM * warpsN; ++w) {
-        const int wm = w % warpsM, wn = w / warpsM;
-        int ai = TI, aj = TJ;
-        if (skip) {
-            const int64_t mrem = mr - (int64_t)wm * c.WM, nrem = nc - (int64_t)wn * c.WN;
-            ai = mrem >= c.WM ? TI : (mrem <= 0 ? 0 : (int)((mrem + 7) / 8));
-            aj = nrem >= c.WN ? TJ : (nrem <= 0 ? 0 : (int)((nrem + 7) / 8));
-        }
-        load[w & 3] += ai * aj;
-    }
-    return std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
-}
-
 // Pick the tile configuration and split-K factor that minimise a simple time model:
 // waves(tiles*split / SMs) * (stages per CTA + fixed prologue/epilogue cost) * tile area * tile cost.
-// For the small configurations the area is what a ragged / skinny tile actually computes (sub-tile skipping).
-// (A cycle-accurate variant of this model with an HBM floor was measured at BASELINE config 3 and picked
-// worse configurations for the 400x400x10^4 and M >> N, K shapes: 6.99 ms of GEMM time per sweep against
-// 6.85 ms -- profiles/r02/session_r02f.log -- so the empirical form stays.)
+// (Two refinements were measured at BASELINE config 3 and rejected: a cycle-level model with an HBM floor
+// and up to 256 splits -- 6.99 ms of GEMM time per sweep against 6.85 ms, profiles/r02/session_r02f.log --
+// and counting only the computed sub-tiles of partial tiles -- 7.41 ms, profiles/r02/gemm_list_c3_r02h.txt.
+// The skinny products of the sweep are bandwidth bound and want a different kernel, not a different tile.)
 void choose_cfg(jues_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t batch, bool allow_split,
                 int* cfg_out, int* split_out) {
     int best = 0, best_split = 1;
@@ -113,10 +93,7 @@ void choose_cfg(jues_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t batch, b
     for (int c = 0; c < kNumCfgs; ++c) {
         const double tiles = (double)((M + kCfgs[c].BM - 1) / kCfgs[c].BM) *
                              (double)((N + kCfgs[c].BN - 1) / kCfgs[c].BN) * (double)batch;
-        double area = (double)kCfgs[c].BM * kCfgs[c].BN;
-        if (M < kCfgs[c].BM || N < kCfgs[c].BN)      // every tile is partial: count what it computes
-            area = std::max(0.25 * area, 256.0 * smsp_load(kCfgs[c], std::min<int64_t>(M, kCfgs[c].BM),
-                                                           std::min<int64_t>(N, kCfgs[c].BN)));
+        const double area = (double)kCfgs[c].BM * kCfgs[c].BN;
         int max_split = 1;
         if (allow_split && tiles < sms) max_split = (int)std::min<double>(64.0, std::max(1.0, KT / 8.0));
         for (int sp = 1; sp <= max_split; sp = sp < 4 ? sp + 1 : sp * 2) {
@@ -219,8 +196,8 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
         Timer* tk = nullptr;
         if (ctx->trace >= 2) {
             char nm[48];
-            snprintf(nm, sizeof nm, "gemm %lldx%lldx%lldx%lld", (long long)g.M, (long long)g.N, (long long)g.K,
-                     (long long)g.batch);
+            snprintf(nm, sizeof nm, "gemm %lldx%lldx%lldx%lld %c%c%s", (long long)g.M, (long long)g.N, (long long)g.K,
+                     (long long)g.batch, g.transA ? 'T' : 'N', g.transB ? 'T' : 'N', g.beta != 0.0 ? "+" : "");
             tk = new Timer(ctx, nm);
         }
         fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(mapA, mapB, p);

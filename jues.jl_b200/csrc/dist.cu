@@ -7,6 +7,8 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <thread>
+#include <functional>
 
 namespace jues {
 
@@ -17,6 +19,8 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
@@ -49,6 +53,8 @@ void load_nccl() {
     g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))sym("ncclCommInitAll");
+    g_nccl.CommAbort = (decltype(g_nccl.CommAbort))sym("ncclCommAbort");
     g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
     g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
@@ -133,9 +139,114 @@ double all_reduce_scalar(jues_ctx* ctx, double x) {
     return r;
 }
 
+// Run `fn(member, is_leader)` on every member of the leader's group, one host thread per GPU (the leader's
+// share on the calling thread).  Returns the first non-zero status; its message lands in the leader's
+// last_error.  If a member fails while the others wait in a collective, the communicators are aborted so
+// that nobody hangs (the group is unusable afterwards and reports JUES_B200_ENCCL).
+int group_run(jues_ctx* lead, const std::function<int(jues_ctx*, bool)>& fn) {
+    std::vector<jues_ctx*>& g = *lead->group;
+    const int n = (int)g.size();
+    std::vector<int> rc((size_t)n, 0);
+    for (jues_ctx* m : g) m->in_group_call = true;
+    std::vector<std::thread> th;
+    auto body = [&](int r) {
+        cudaSetDevice(g[r]->device);
+        rc[r] = fn(g[r], r == 0);
+        if (rc[r] != 0 && g_nccl.CommAbort)
+            for (jues_ctx* m : g)
+                if (m->nccl_comm) { g_nccl.CommAbort((ncclComm_t)m->nccl_comm); m->nccl_comm = nullptr; }
+    };
+    for (int r = 1; r < n; ++r) th.emplace_back(body, r);
+    body(0);
+    for (auto& t : th) t.join();
+    for (jues_ctx* m : g) m->in_group_call = false;
+    cudaSetDevice(lead->device);
+    for (int r = 0; r < n; ++r)
+        if (rc[r] != 0) {
+            if (r != 0) lead->last_error = "rank " + std::to_string(r) + ": " + g[r]->last_error;
+            return rc[r];
+        }
+    return 0;
+}
+
 }  // namespace jues
 
 using namespace jues;
+
+extern "C" int jues_b200_init_multi(jues_ctx** out, int ngpu) {
+    if (!out) return JUES_B200_EINVAL;
+    *out = nullptr;
+    std::vector<jues_ctx*>* members = new std::vector<jues_ctx*>();
+    auto fail = [&](int code, const std::string& msg) {
+        for (jues_ctx* m : *members) { m->group = nullptr; jues_b200_finalize(m); }
+        delete members;
+        g_init_error = msg;
+        return code;
+    };
+    try {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            return fail(JUES_B200_ECUDA, "no CUDA device available; jues_b200 has no CPU fallback");
+        }
+        if (ngpu <= 0) ngpu = ndev;
+        if (ngpu > ndev) return fail(JUES_B200_EINVAL, "jues_b200_init_multi: more GPUs requested than visible");
+        for (int r = 0; r < ngpu; ++r) {
+            jues_ctx* m = nullptr;
+            const int rc = jues_b200_init(&m, r);
+            if (rc != 0) return fail(rc, g_init_error);
+            members->push_back(m);
+        }
+        jues_ctx* lead = (*members)[0];
+        if (ngpu > 1) {
+            load_nccl();
+            std::vector<ncclComm_t> comms((size_t)ngpu);
+            std::vector<int> devs((size_t)ngpu);
+            for (int r = 0; r < ngpu; ++r) devs[r] = r;
+            nccl_check(g_nccl.CommInitAll(comms.data(), ngpu, devs.data()), "ncclCommInitAll");
+            for (int r = 0; r < ngpu; ++r) {
+                (*members)[r]->nccl_comm = comms[r];
+                (*members)[r]->rank = r;
+                (*members)[r]->nranks = ngpu;
+            }
+        }
+        for (jues_ctx* m : *members) m->leader = lead;
+        lead->group = members;
+        if (ngpu > 1) {
+            // first collectives set up the NVLink / peer connections: here, not inside a timed call
+            const int rc = group_run(lead, [&](jues_ctx* m, bool) {
+                try {
+                    double* slot = m->red_dev + m->red_cap - 2;
+                    JUES_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), m->stream));
+                    all_reduce_sum(m, slot, 1);
+                    all_gather_inplace(m, m->red_dev, 1);
+                    std::vector<size_t> off((size_t)m->nranks), cnt((size_t)m->nranks, 1);
+                    for (int d = 0; d < m->nranks; ++d) off[d] = (size_t)d;
+                    all_to_all_v(m, m->red_dev, off.data(), cnt.data(), m->red_dev + m->nranks, off.data(), cnt.data());
+                    JUES_CUDA(cudaStreamSynchronize(m->stream));
+                    return 0;
+                } catch (const Error& e) {
+                    m->last_error = e.what();
+                    return e.code;
+                }
+            });
+            if (rc != 0) {
+                const std::string msg = lead->last_error;
+                lead->group = nullptr;
+                return fail(rc, msg);
+            }
+        }
+        *out = lead;
+        return JUES_B200_OK;
+    } catch (const Error& e) {
+        return fail(e.code, e.what());
+    }
+}
+
+extern "C" int jues_b200_group_size(jues_ctx* ctx) {
+    if (!ctx) return JUES_B200_EINVAL;
+    return ctx->group ? (int)ctx->group->size() : 1;
+}
 
 extern "C" int jues_b200_nccl_unique_id(unsigned char id_out[128]) {
     if (!id_out) return JUES_B200_EINVAL;

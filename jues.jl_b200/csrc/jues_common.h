@@ -79,6 +79,7 @@ struct Arena {
     size_t bytes = 0;
     std::map<size_t, size_t> free_by_off;   // offset -> length of free runs, coalesced on release
     size_t live = 0, peak = 0;
+    long long misses = 0;                   // requests that did not fit (served by the pool / block cache)
     bool has(const void* p) const {
         return base && (const char*)p >= (const char*)base && (const char*)p < (const char*)base + bytes;
     }
@@ -96,6 +97,7 @@ struct Arena {
             if (live > peak) peak = live;
             return (double*)((char*)base + off);
         }
+        ++misses;
         return nullptr;
     }
     void give(const void* p, size_t n) {
@@ -151,6 +153,11 @@ struct jues_ctx {
     void* nccl_comm = nullptr;
     void* nccl_lib = nullptr;
     void* perm_cache = nullptr;   // jues::PermCache of the running calculation (contract.h)
+    // single-process multi-GPU (jues_b200_init_multi): the leader (rank 0) context lists every member,
+    // itself included; an entry point called on the leader runs on all members, one host thread per GPU
+    std::vector<jues_ctx*>* group = nullptr;   // non-null on the leader only
+    jues_ctx* leader = nullptr;                // non-null on members (the leader points to itself)
+    bool in_group_call = false;
     // diagnostics (environment, read once in jues_b200_init): JUES_B200_BIG_MB moves the pool / cudaMalloc
     // threshold of DBuf, JUES_B200_SYNC_COMM=1 drains the stream around every collective
     size_t big_bytes = size_t(64) << 20;

@@ -46,8 +46,18 @@ function set_backend(b::Symbol)
     if b == :b200 && ctx[] == C_NULL
         lib[] = Libdl.dlopen(LIBPATH)            # throws if the library is missing
         c = Ref{Ptr{Cvoid}}(C_NULL)
-        dev = parse(Int, get(ENV, "LOCAL_RANK", "0"))
-        rc = ccall(Libdl.dlsym(lib[], :jues_b200_init), Cint, (Ref{Ptr{Cvoid}}, Cint), c, dev)
+        if haskey(ENV, "LOCAL_RANK")
+            # one process per GPU (torchrun / mpirun / Distributed): this process drives its own device and
+            # the launcher attaches the communicator with jues_b200_init_dist
+            dev = parse(Int, ENV["LOCAL_RANK"])
+            rc = ccall(Libdl.dlsym(lib[], :jues_b200_init), Cint, (Ref{Ptr{Cvoid}}, Cint), c, dev)
+        else
+            # the reference's own way of running (Input.exec calls com(JuWfn; ...) once, from one task,
+            # Input.jl:58-71): ONE handle in front of every visible GPU -- JUES_B200_GPUS limits the count --
+            # and the library fans the sharding entry points out over them, one host thread per GPU
+            ngpu = parse(Int, get(ENV, "JUES_B200_GPUS", "0"))
+            rc = ccall(Libdl.dlsym(lib[], :jues_b200_init_multi), Cint, (Ref{Ptr{Cvoid}}, Cint), c, ngpu)
+        end
         rc == 0 || error("jues_b200_init failed ($rc): " *
                          unsafe_string(ccall(Libdl.dlsym(lib[], :jues_b200_last_error), Cstring, (Ptr{Cvoid},), C_NULL)))
         ctx[] = c[]
