@@ -578,7 +578,9 @@ def gpu_arm(args, rank, world):
         worst = max(d_run, d_e2e or 0.0)
         parity = {"status": "ok" if worst <= E_TOL else "FAILED", "max_abs_dE": worst, "tol": E_TOL,
                   "max_abs_dE_timed_run": d_run, "sweeps_compared": n, "abs_dE_e2e_40_sweeps": d_e2e,
-                  "golden": gold_path, "oracle": "oracle/jues_oracle.py (literal RCCSD.jl:150-289), tests/golden/make_bench_golden.py"}
+                  "golden": gold_path,
+                  "oracle": (str(gold["model"]) if "model" in gold.files else
+                             "oracle/jues_oracle.py (literal RCCSD.jl:150-289)") + ", tests/golden/make_bench_golden.py"}
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only), bounded sample ------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

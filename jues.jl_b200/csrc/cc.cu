@@ -269,7 +269,6 @@ struct CC {
 
     // one Jacobi sweep: (T1,T2) -> (T1n,T2n), then swap
     void iterate() {
-        const size_t n2 = (size_t)(o * o * v * v);
         const Ten t = T1, T = T2;
         const Ten tS = last_slab(t, b0, vs), T_S = last_slab(T, b0, vs);
         const Ten V_S = last_slab(V, b0, vs), Vt_S = last_slab(Vt, b0, vs), J_S = last_slab(J, b0, vs);

@@ -130,6 +130,20 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
     JUES_REQUIRE(g.A && g.B && g.C, "GEMM null operand");
     JUES_REQUIRE(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "GEMM dimension too large");
     JUES_REQUIRE(g.ldc >= g.M, "GEMM ldc < M");
+    Timer* tk = nullptr;
+    if (ctx->trace >= 2) {
+        char nm[48];
+        snprintf(nm, sizeof nm, "gemm %lldx%lldx%lldx%lld %c%c%s", (long long)g.M, (long long)g.N, (long long)g.K,
+                 (long long)g.batch, g.transA ? 'T' : 'N', g.transB ? 'T' : 'N', g.beta != 0.0 ? "+" : "");
+        tk = new Timer(ctx, nm);
+    }
+    // bandwidth-bound skinny products go to the streaming FMA kernels (skinny.cu)
+    if (skinny_gemm(ctx, g)) {
+        delete tk;
+        ctx->stats.gemm_flops += 2.0 * (double)g.M * (double)g.N * (double)g.K;
+        ctx->stats.gemm_launches += 1;
+        return;
+    }
     const bool a_kc = g.transA;   // A stored K x M
     const bool b_kc = !g.transB;  // B stored K x N
     int cfg = 0, ksplit = 1;
@@ -192,17 +206,8 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
     // cost ~1-3 % on long-K tiles (static tile assignment, extra live registers), so: short K only.
     const bool persistent = persistent_gemm() && kt_per_split <= 32 && total > sms;
     const long long grid = persistent ? sms : total;
-    {
-        Timer* tk = nullptr;
-        if (ctx->trace >= 2) {
-            char nm[48];
-            snprintf(nm, sizeof nm, "gemm %lldx%lldx%lldx%lld %c%c%s", (long long)g.M, (long long)g.N, (long long)g.K,
-                     (long long)g.batch, g.transA ? 'T' : 'N', g.transB ? 'T' : 'N', g.beta != 0.0 ? "+" : "");
-            tk = new Timer(ctx, nm);
-        }
-        fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(mapA, mapB, p);
-        delete tk;
-    }
+    fn<<<(unsigned)grid, threads, smem, ctx->stream>>>(mapA, mapB, p);
+    delete tk;
     JUES_CUDA(cudaGetLastError());
     ctx->stats.gemm_flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch;
     ctx->stats.gemm_launches += 1;

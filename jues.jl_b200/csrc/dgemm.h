@@ -23,6 +23,10 @@ struct GemmCall {
 // strideB even.  C has no alignment requirement beyond 8 bytes.
 void dgemm(jues_ctx* ctx, const GemmCall& g);
 
+// Streaming FMA kernels for bandwidth-bound skinny products (skinny.cu); returns false when the shape is not
+// one of theirs (the caller then uses the tile kernel).  JUES_B200_NO_SKINNY=1 switches them off.
+bool skinny_gemm(jues_ctx* ctx, const GemmCall& g);
+
 int dgemm_num_configs();
 const char* dgemm_config_name(int cfg);
 

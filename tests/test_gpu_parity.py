@@ -405,3 +405,21 @@ def test_sampled_elements_of_a_large_generated_transform(ctx):
     for k, (i, j) in enumerate(pairs):
         ref = Cav.T @ h[k] @ Cav                               # <ij|ab> = (ia|jb)
         assert np.abs(ijab[i, j] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) + 1e-13, (i, j)
+
+
+# ---- the streaming kernels for skinny products (csrc/skinny.cu) ---------------------------------------
+@pytest.mark.parametrize("tA,tB,M,N,K", [
+    ("N", "N", 4100, 20, 100), ("N", "T", 4100, 7, 33), ("T", "N", 3000, 1, 2000), ("T", "T", 2500, 20, 64),
+    ("N", "N", 5000, 100, 20), ("N", "N", 4096, 130, 17), ("T", "N", 2049, 3, 5),
+    ("N", "N", 20, 4100, 100), ("N", "T", 20, 4100, 100), ("T", "N", 3, 5000, 40), ("T", "T", 100, 3000, 20),
+    ("N", "T", 20, 100, 9000), ("N", "T", 20, 20, 10000), ("N", "T", 100, 100, 8200), ("N", "T", 7, 33, 8500)])
+@pytest.mark.parametrize("beta", [0.0, 0.3])
+def test_gemm_skinny_streaming(ctx, tA, tB, M, N, K, beta):
+    rng = np.random.default_rng(M + 7 * N + 13 * K)
+    A = rng.standard_normal((K, M) if tA == "T" else (M, K))
+    B = rng.standard_normal((N, K) if tB == "T" else (K, N))
+    C0 = rng.standard_normal((M, N))
+    ref = 1.7 * (A.T if tA == "T" else A) @ (B.T if tB == "T" else B) + beta * C0
+    got = ctx.gemm(tA, tB, 1.7, A, B, beta, np.asfortranarray(C0.copy()))
+    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.sqrt(K)
+    assert ctx.gemm_stress(tA, tB, M, N, K, 1, reps=3) == (0, 0.0)
