@@ -145,24 +145,27 @@ void contract(jues_ctx* ctx, double alpha, const Ten& A, const char* ia, const T
     const double* pa = A.p;
     const double* pb = B.p;
     bool a_t, b_t;  // BLAS transposition flags
+    // A product with a huge K and small M, N is bandwidth bound: the streaming kernel (skinny.cu) wants both
+    // operands contiguous along their SMALL index, so an operand that must be re-ordered anyway is put there
+    const bool khuge = M <= 128 && N <= 128 && M * N <= 4096 && K >= 8192;
     if (is_concat(sa, mord, kord)) a_t = false;       // stored M x K
     else if (is_concat(sa, kord, mord)) a_t = true;   // stored K x M
     else {
-        // permute into K-contiguous form [K..., M...]
-        const std::string tgt = kord + mord;
+        // permute into K-contiguous form [K..., M...] (K-huge products: [M..., K...])
+        const std::string tgt = khuge ? mord + kord : kord + mord;
         int64_t td[4] = {1, 1, 1, 1};
         for (size_t q = 0; q < tgt.size(); ++q) td[q] = extent_of(tgt[q], A, ia, B, ib, C, ic);
         pa = permuted_operand(ctx, A, ia, tgt, td, tmpA);
-        a_t = true;
+        a_t = !khuge;
     }
     if (is_concat(sb, kord, nord)) b_t = false;       // stored K x N
     else if (is_concat(sb, nord, kord)) b_t = true;   // stored N x K
     else {
-        const std::string tgt = kord + nord;
+        const std::string tgt = khuge ? nord + kord : kord + nord;
         int64_t td[4] = {1, 1, 1, 1};
         for (size_t q = 0; q < tgt.size(); ++q) td[q] = extent_of(tgt[q], A, ia, B, ib, C, ic);
         pb = permuted_operand(ctx, B, ib, tgt, td, tmpB);
-        b_t = false;
+        b_t = khuge;
     }
 
     GemmCall g;

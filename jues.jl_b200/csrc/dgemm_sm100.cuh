@@ -249,14 +249,6 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = 0; i < TI; ++i)
 #pragma unroll
             for (int j = 0; j < TJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        // 8-row / 8-column groups of this warp's tile that hold any element of C (warp-uniform)
-        const int mrem = p.M - (m0 + wm * WM), nrem = p.N - (n0 + wn * WN);
-        const int ai = mrem >= WM ? TI : (mrem <= 0 ? 0 : (mrem + 7) >> 3);
-        const int aj = nrem >= WN ? TJ : (nrem <= 0 ? 0 : (nrem + 7) >> 3);
-        // only the small tile configurations carry the skipping path (the 80..128 x 128 tiles have no
-        // registers to spare for it: 168 per thread, and they are chosen for large, full tiles anyway)
-        constexpr bool kSkip = BM * BN <= 8192;
-        const bool full_tile = !kSkip || ((ai == TI) && (aj == TJ));
 
         // Release protocol.  A stage may go back to the TMA producer only when every LDS that reads it
         // has RETURNED its data.  Neither `asm volatile` nor the release semantics of mbarrier.arrive
@@ -278,47 +270,21 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             s_prev = s;
             const uint32_t st = smem_base + s * L::STAGE_BYTES;
-            if (full_tile) {
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
+            for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-                    for (int ss = 0; ss < 2; ++ss) {
-                        double a[TI], b[TJ];
+                for (int ss = 0; ss < 2; ++ss) {
+                    double a[TI], b[TJ];
 #pragma unroll
-                        for (int i = 0; i < TI; ++i)
-                            a[i] = lds64(st + offA[ss][kb][i & 1] + (i >> 1) * 2048);
+                    for (int i = 0; i < TI; ++i)
+                        a[i] = lds64(st + offA[ss][kb][i & 1] + (i >> 1) * 2048);
 #pragma unroll
-                        for (int j = 0; j < TJ; ++j)
-                            b[j] = lds64(st + offB[ss][kb][j & 1] + (j >> 1) * 2048);
+                    for (int j = 0; j < TJ; ++j)
+                        b[j] = lds64(st + offB[ss][kb][j & 1] + (j >> 1) * 2048);
 #pragma unroll
-                        for (int i = 0; i < TI; ++i)
+                    for (int i = 0; i < TI; ++i)
 #pragma unroll
-                            for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                    }
-                }
-            } else {
-                // ragged / skinny tile: 8x8 sub-tiles that lie entirely beyond M or N are skipped (their
-                // operands are TMA zero fill).  A 20 x 100 x K product in a 48x128 tile then issues 39
-                // DMMAs per k-quad instead of 96 -- such shapes are DMMA-issue bound otherwise.
-#pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-                    for (int ss = 0; ss < 2; ++ss) {
-                        double a[TI], b[TJ];
-#pragma unroll
-                        for (int i = 0; i < TI; ++i)
-                            if (i < ai) a[i] = lds64(st + offA[ss][kb][i & 1] + (i >> 1) * 2048);
-#pragma unroll
-                        for (int j = 0; j < TJ; ++j)
-                            if (j < aj) b[j] = lds64(st + offB[ss][kb][j & 1] + (j >> 1) * 2048);
-#pragma unroll
-                        for (int i = 0; i < TI; ++i)
-                            if (i < ai) {
-#pragma unroll
-                                for (int j = 0; j < TJ; ++j)
-                                    if (j < aj) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                            }
-                    }
+                        for (int j = 0; j < TJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                 }
             }
         }

@@ -1,17 +1,19 @@
-// Streaming kernels for the "skinny" products of the path: C = alpha * op(A) op(B) + beta * C where one
-// operand is large and the flop / byte ratio is far below the FP64 ridge (K <= ~100 or min(M, N) <= ~20; the
-// t1-dressed integral terms of RCCSD.jl:187-259 and the o^2 v^3-sized intermediates).  The TMA + DMMA tile
-// kernel is 3-4x above the HBM floor on these whatever its configuration (profiles/r02/gemm_autotune.log:
-// tile padding makes it DMMA-issue bound, and few, short tiles cannot keep enough bytes in flight).  Here the
-// large operand is read exactly once, coalesced, by plain FP64 FMA threads; the small operand lives in shared
-// memory.  Results are deterministic (fixed summation order, no atomics).
+// Streaming kernels for two families of bandwidth-bound products of the sweep, where the TMA + DMMA tile
+// kernel is 3-4x above the HBM floor whatever its configuration (profiles/r02/gemm_autotune.log: tile padding
+// makes it DMMA-issue bound and few short tiles cannot keep enough bytes in flight):
 //
-//   rows kernels : out(r, c) = sum_k L(r, k) S(k, c),  r huge, c <= 256, K moderate.  One thread per row and
-//                  group of columns.  L is either r-contiguous ("N": loaded straight, coalesced over rows) or
-//                  k-contiguous ("T": 32-deep k tiles transposed through shared memory).  Generic strides for
-//                  S and out make the same kernels serve C = A B with M huge and (transposed) with N huge.
-//   K-huge kernel: C (M x N, both <= 128) = A (M x K, M-contiguous) B^T (N x K, N-contiguous), K >= 8192,
-//                  split over ~2 CTAs per SM; partial tiles are summed by splitk_reduce in a fixed order.
+//   * matrix-vector products  y[r] = alpha * sum_k L[k + r*ld] x[k] + beta * y[r]   (N == 1, op(A) = A^T):
+//     the t1-contractions of the ov^3 / o^2v^2 integrals (RCCSD.jl:187-210, 248-259).  One warp per row,
+//     16-byte loads along k, x in shared memory, shuffle reduction: one pass over L at HBM speed.
+//   * K-huge products  C (M x N, both <= 128) = A (M x K) B^T (N x K), K >= 8192, both operands dense and
+//     contiguous along their small index (Fae / Fmi / T1 residual terms: K = o v^2 or o^2 v).  K is split over
+//     ~2 CTAs per SM; each streams its contiguous slices of A and B through a double-buffered cp.async ring
+//     and accumulates a register micro-tile per thread; the partial tiles are summed by splitk_reduce in a
+//     fixed order.
+//
+// Deterministic (fixed summation order, no atomics).  A first, general "one thread per row" family for
+// M >> N, K products was measured slower than the tile kernel and is not kept
+// (profiles/r02/gemm_list_c3_r02i.txt).
 #include "dgemm.h"
 #include "tensor_ops.h"
 
@@ -21,143 +23,117 @@ namespace jues {
 
 namespace {
 
-struct RowsArgs {
-    long long R;            // rows of the large operand / of the output
-    int K, nc;              // inner extent, number of output columns
-    const double* L; long long ldl;       // large operand: "N": L[r + k*ldl], "T": L[k + r*ldl]
-    const double* S; long long ssk, ssc;  // small operand S(k, c) at S[k*ssk + c*ssc]
-    double* O; long long sor, soc;        // out(r, c) at O[r*sor + c*soc]
+// ---- matrix-vector ------------------------------------------------------------------------------------------
+struct GemvArgs {
+    long long R;            // rows
+    int K;
+    const double* L; long long ldl;   // L[k + r*ldl]
+    const double* x; long long sx;    // x[k*sx]
+    double* y; long long sy;          // y[r*sy]
     double alpha, beta;
-    int kc;                 // k-chunk held in shared memory at a time
 };
 
-constexpr int kTX = 64;     // rows per block
-
-// NCG columns per thread; blockDim = (kTX, TY), TY * NCG >= nc.
-template <int NCG, bool L_KCONTIG>
-__global__ void __launch_bounds__(kTX * 8) skinny_rows_kernel(RowsArgs a) {
-    extern __shared__ double sm[];
-    const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
-    const int ncp = TY * NCG;                       // padded column count of the shared S chunk
-    double* Ss = sm;                                // [kc][ncp]
-    double* Lt = sm + (size_t)a.kc * ncp;           // [32][kTX + 1]   (L_KCONTIG only)
-    const long long r0 = (long long)blockIdx.x * kTX;
-    const long long r = r0 + tx;
-    const bool live = r < a.R;
-    const int c0 = ty * NCG;
-    double acc[NCG];
-#pragma unroll
-    for (int c = 0; c < NCG; ++c) acc[c] = 0.0;
-    const int nthreads = kTX * TY, tid = ty * kTX + tx;
-    for (int k0 = 0; k0 < a.K; k0 += a.kc) {
-        const int kn = min(a.kc, a.K - k0);
-        __syncthreads();
-        for (int e = tid; e < kn * ncp; e += nthreads) {
-            const int c = e % ncp, k = e / ncp;
-            Ss[e] = c < a.nc ? a.S[(long long)(k0 + k) * a.ssk + (long long)c * a.ssc] : 0.0;
-        }
-        __syncthreads();
-        if (!L_KCONTIG) {
-            if (live) {
-                const double* lp = a.L + r + (long long)k0 * a.ldl;
-#pragma unroll 4
-                for (int k = 0; k < kn; ++k) {
-                    const double x = lp[(long long)k * a.ldl];
-                    const double* s = Ss + k * ncp + c0;
-#pragma unroll
-                    for (int c = 0; c < NCG; ++c) acc[c] = fma(x, s[c], acc[c]);
-                }
+template <bool VEC>
+__global__ void __launch_bounds__(256) skinny_gemv_kernel(GemvArgs a) {
+    extern __shared__ double xs[];    // [K]
+    for (int k = threadIdx.x; k < a.K; k += blockDim.x) xs[k] = a.x[(long long)k * a.sx];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (long long r = (long long)blockIdx.x * wpb + warp; r < a.R; r += (long long)gridDim.x * wpb) {
+        const double* row = a.L + r * a.ldl;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (VEC) {
+            const double2* row2 = reinterpret_cast<const double2*>(row);
+            const double2* x2 = reinterpret_cast<const double2*>(xs);
+            const int K2 = a.K >> 1;
+            int k = lane;
+            for (; k + 96 < K2; k += 128) {     // four independent 16-byte loads in flight per lane
+                const double2 v0 = row2[k], v1 = row2[k + 32], v2 = row2[k + 64], v3 = row2[k + 96];
+                const double2 w0 = x2[k], w1 = x2[k + 32], w2 = x2[k + 64], w3 = x2[k + 96];
+                s0 = fma(v0.x, w0.x, fma(v0.y, w0.y, s0));
+                s1 = fma(v1.x, w1.x, fma(v1.y, w1.y, s1));
+                s2 = fma(v2.x, w2.x, fma(v2.y, w2.y, s2));
+                s3 = fma(v3.x, w3.x, fma(v3.y, w3.y, s3));
+            }
+            for (; k < K2; k += 32) {
+                const double2 v = row2[k], w = x2[k];
+                s0 = fma(v.x, w.x, fma(v.y, w.y, s0));
             }
         } else {
-            for (int kt = 0; kt < kn; kt += 32) {
-                const int kw = min(32, kn - kt);
-                __syncthreads();
-                // tile [kTX rows][32 k]: lanes along k (contiguous), warps over rows
-                for (int e = tid; e < kTX * 32; e += nthreads) {
-                    const int kk = e & 31, rr = e >> 5;
-                    const long long row = r0 + rr;
-                    Lt[kk * (kTX + 1) + rr] = (kk < kw && row < a.R) ? a.L[(long long)(k0 + kt + kk) + row * a.ldl] : 0.0;
-                }
-                __syncthreads();
-#pragma unroll 4
-                for (int kk = 0; kk < kw; ++kk) {
-                    const double x = Lt[kk * (kTX + 1) + tx];
-                    const double* s = Ss + (kt + kk) * ncp + c0;
-#pragma unroll
-                    for (int c = 0; c < NCG; ++c) acc[c] = fma(x, s[c], acc[c]);
-                }
-            }
+            for (int k = lane; k < a.K; k += 32) s0 = fma(row[k], xs[k], s0);
         }
-    }
-    if (live) {
+        double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
-        for (int c = 0; c < NCG; ++c) {
-            if (c0 + c < a.nc) {
-                double* o = a.O + r * a.sor + (long long)(c0 + c) * a.soc;
-                const double v = a.alpha * acc[c];
-                *o = a.beta == 0.0 ? v : v + a.beta * *o;
-            }
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        if (lane == 0) {
+            double* o = a.y + r * a.sy;
+            const double v = a.alpha * s;
+            *o = a.beta == 0.0 ? v : v + a.beta * *o;
         }
     }
 }
 
-template <int NCG>
-void launch_rows(jues_ctx* ctx, const RowsArgs& a, bool kcontig, int TY, size_t smem) {
-    const dim3 block(kTX, TY);
-    const unsigned grid = (unsigned)((a.R + kTX - 1) / kTX);
-    if (kcontig) {
-        if (ctx->smem_attr_done.insert((const void*)skinny_rows_kernel<NCG, true>).second)
-            JUES_CUDA(cudaFuncSetAttribute(skinny_rows_kernel<NCG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        skinny_rows_kernel<NCG, true><<<grid, block, smem, ctx->stream>>>(a);
-    } else {
-        if (ctx->smem_attr_done.insert((const void*)skinny_rows_kernel<NCG, false>).second)
-            JUES_CUDA(cudaFuncSetAttribute(skinny_rows_kernel<NCG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        skinny_rows_kernel<NCG, false><<<grid, block, smem, ctx->stream>>>(a);
+// y[r] = alpha * sum_k L[r + k*ldl] x[k] + beta * y[r]: the matrix is contiguous along r.  Block = 32 rows x 8
+// k-groups: a warp reads 32 consecutive rows of one k (256 bytes), the eight groups stride through k, their
+// partial sums are added in a fixed order through shared memory.
+__global__ void __launch_bounds__(256) skinny_gemv_n_kernel(GemvArgs a) {
+    extern __shared__ double xs[];    // [K] + [8][32]
+    double* part = xs + a.K;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < a.K; k += blockDim.x) xs[k] = a.x[(long long)k * a.sx];
+    __syncthreads();
+    const long long r = (long long)blockIdx.x * 32 + tx;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (r < a.R) {
+        const double* col = a.L + r;
+        int k = ty;
+        for (; k + 24 < a.K; k += 32) {
+            const double v0 = col[(long long)k * a.ldl], v1 = col[(long long)(k + 8) * a.ldl];
+            const double v2 = col[(long long)(k + 16) * a.ldl], v3 = col[(long long)(k + 24) * a.ldl];
+            s0 = fma(v0, xs[k], s0); s1 = fma(v1, xs[k + 8], s1);
+            s2 = fma(v2, xs[k + 16], s2); s3 = fma(v3, xs[k + 24], s3);
+        }
+        for (; k < a.K; k += 8) s0 = fma(col[(long long)k * a.ldl], xs[k], s0);
     }
-    JUES_CUDA(cudaGetLastError());
+    part[ty * 32 + tx] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (ty == 0 && r < a.R) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += part[q * 32 + tx];
+        double* o = a.y + r * a.sy;
+        const double v = a.alpha * s;
+        *o = a.beta == 0.0 ? v : v + a.beta * *o;
+    }
 }
 
-void rows_product(jues_ctx* ctx, RowsArgs a, bool kcontig) {
-    // columns per thread and column groups per block: NCG * TY >= nc, TY <= 8
-    int NCG = a.nc <= 8 ? (a.nc <= 1 ? 1 : (a.nc <= 4 ? 4 : 8)) : (a.nc <= 64 ? 8 : (a.nc <= 128 ? 16 : 32));
-    int TY = (a.nc + NCG - 1) / NCG;
-    if (TY > 8) { NCG = 32; TY = (a.nc + 31) / 32; }
-    const int ncp = TY * NCG;
-    // shared memory: S chunk [kc][ncp] (<= 40 KB so that several blocks share an SM) + the transposed L tile
-    const size_t tile = kcontig ? (size_t)32 * (kTX + 1) * 8 : 0;
-    int kc = (int)std::max<size_t>(32, (size_t(40) << 10) / ((size_t)ncp * 8));
-    kc = std::min(a.K, kc & ~31);
-    if (kc <= 0) kc = std::min(a.K, 32);
-    a.kc = kc;
-    const size_t smem = (size_t)kc * ncp * 8 + tile;
-    switch (NCG) {
-        case 1: launch_rows<1>(ctx, a, kcontig, TY, smem); break;
-        case 4: launch_rows<4>(ctx, a, kcontig, TY, smem); break;
-        case 8: launch_rows<8>(ctx, a, kcontig, TY, smem); break;
-        case 16: launch_rows<16>(ctx, a, kcontig, TY, smem); break;
-        default: launch_rows<32>(ctx, a, kcontig, TY, smem); break;
-    }
-    ctx->stats.aux_launches += 1;
-}
-
-// ---- K huge, M and N small:  W[z] (M x N) = sum_{k in chunk z} A[:, k] B[:, k]^T ------------------------
+// ---- K huge, M and N small:  W[z] (M x N) = sum_{k in chunk z} A[:, k] B[:, k]^T --------------------------
 struct KHugeArgs {
-    int M, N;
-    long long K, kper;      // k range per CTA
-    const double* A; long long lda;   // A[m + k*lda]
-    const double* B; long long ldb;   // B[n + k*ldb]
-    double* W;              // [gridDim.x][M*N]
+    int M, N;               // both even
+    long long K, kper;      // k range per CTA (a multiple of kKC)
+    const double* A;        // dense M x K (lda == M), 16-byte aligned
+    const double* B;        // dense N x K (ldb == N), 16-byte aligned
+    double* W;              // [M*N][ldz]: element e of CTA z at W[e*ldz + z] (slices contiguous per element)
+    int ldz;
 };
 
-constexpr int kKC = 32;     // k-rows staged per step
+constexpr int kKC = 32;     // k-columns staged per step
 
-template <int TM, int TN>
-__global__ void __launch_bounds__(256) skinny_khuge_kernel(KHugeArgs a) {
-    extern __shared__ double sm[];
-    const int Mp = (a.M + TM - 1) / TM * TM, Np = (a.N + TN - 1) / TN * TN;
-    double* As = sm;                       // [kKC][Mp]
-    double* Bs = sm + kKC * Mp;            // [kKC][Np]
-    const int gm = Mp / TM, gn = Np / TN;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// The slices A[:, k0 .. k0+kn) and B[:, k0 .. k0+kn) are contiguous runs of kn*M and kn*N doubles.
+template <int TM, int TN, int THREADS>
+__global__ void __launch_bounds__(THREADS) skinny_khuge_kernel(KHugeArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int M = a.M, N = a.N;
+    const int stage = kKC * (M + N);               // doubles per stage: [A chunk | B chunk]
+    const int gm = (M + TM - 1) / TM, gn = (N + TN - 1) / TN;
     const int tid = threadIdx.x;
     const bool worker = tid < gm * gn;
     const int m0 = (tid % gm) * TM, n0 = (tid / gm) * TN;
@@ -167,100 +143,153 @@ __global__ void __launch_bounds__(256) skinny_khuge_kernel(KHugeArgs a) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
     const long long kb = (long long)blockIdx.x * a.kper, ke = min(a.K, kb + a.kper);
-    for (long long k0 = kb; k0 < ke; k0 += kKC) {
+    const int nsteps = (int)((ke - kb + kKC - 1) / kKC);
+
+    auto issue = [&](int step) {
+        const long long k0 = kb + (long long)step * kKC;
         const int kn = (int)min((long long)kKC, ke - k0);
-        __syncthreads();
-        for (int e = tid; e < kKC * Mp; e += blockDim.x) {
-            const int m = e % Mp, kk = e / Mp;
-            As[e] = (m < a.M && kk < kn) ? a.A[m + (k0 + kk) * a.lda] : 0.0;
-        }
-        for (int e = tid; e < kKC * Np; e += blockDim.x) {
-            const int n = e % Np, kk = e / Np;
-            Bs[e] = (n < a.N && kk < kn) ? a.B[n + (k0 + kk) * a.ldb] : 0.0;
+        double* As = sm + (step & 1) * stage;
+        double* Bs = As + kKC * M;
+        const double* ga = a.A + k0 * M;
+        const double* gb = a.B + k0 * N;
+        const int na = kn * M / 2, nb = kn * N / 2;            // 16-byte pieces (M, N even)
+        for (int e = tid; e < na; e += THREADS) cp_async16(As + 2 * e, ga + 2 * e);
+        for (int e = tid; e < nb; e += THREADS) cp_async16(Bs + 2 * e, gb + 2 * e);
+        // a short last step: the rest of the stage must read as zero
+        for (int e = kn * M + tid; e < kKC * M; e += THREADS) As[e] = 0.0;
+        for (int e = kn * N + tid; e < kKC * N; e += THREADS) Bs[e] = 0.0;
+        cp_async_commit();
+    };
+
+    if (nsteps > 0) issue(0);
+    for (int step = 0; step < nsteps; ++step) {
+        if (step + 1 < nsteps) {
+            issue(step + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
         if (worker) {
+            const double* As = sm + (step & 1) * stage;
+            const double* Bs = As + kKC * M;
 #pragma unroll 4
             for (int kk = 0; kk < kKC; ++kk) {
                 double x[TM], y[TN];
 #pragma unroll
-                for (int i = 0; i < TM; ++i) x[i] = As[kk * Mp + m0 + i];
+                for (int i = 0; i < TM; ++i) x[i] = (m0 + i < M) ? As[kk * M + m0 + i] : 0.0;
 #pragma unroll
-                for (int j = 0; j < TN; ++j) y[j] = Bs[kk * Np + n0 + j];
+                for (int j = 0; j < TN; ++j) y[j] = (n0 + j < N) ? Bs[kk * N + n0 + j] : 0.0;
 #pragma unroll
                 for (int i = 0; i < TM; ++i)
 #pragma unroll
                     for (int j = 0; j < TN; ++j) acc[i][j] = fma(x[i], y[j], acc[i][j]);
             }
         }
+        __syncthreads();      // the stage is refilled two steps later
     }
     if (worker) {
-        double* w = a.W + (long long)blockIdx.x * a.M * a.N;
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
             for (int j = 0; j < TN; ++j)
-                if (m0 + i < a.M && n0 + j < a.N) w[(m0 + i) + (long long)(n0 + j) * a.M] = acc[i][j];
+                if (m0 + i < M && n0 + j < N)
+                    a.W[((long long)(m0 + i) + (long long)(n0 + j) * M) * a.ldz + blockIdx.x] = acc[i][j];
     }
 }
 
-template <int TM, int TN>
+// C[m + n*ldc] = alpha * sum_z W[e*ldz + z] + beta * C: one warp per element, lanes over z in a fixed order
+__global__ void __launch_bounds__(256) skinny_slices_reduce_kernel(const double* __restrict__ W, int ldz, int nz,
+                                                                   int M, int N, double alpha, double beta,
+                                                                   double* __restrict__ C, long long ldc) {
+    const int lane = threadIdx.x & 31;
+    const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= (long long)M * N) return;
+    const double* w = W + e * ldz;
+    double s = 0.0;
+    for (int z = lane; z < nz; z += 32) s += w[z];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+        double* c = C + (e % M) + (e / M) * ldc;
+        *c = beta == 0.0 ? alpha * s : alpha * s + beta * *c;
+    }
+}
+
+template <int TM, int TN, int THREADS>
 void launch_khuge(jues_ctx* ctx, const KHugeArgs& a, int ctas) {
-    const int Mp = (a.M + TM - 1) / TM * TM, Np = (a.N + TN - 1) / TN * TN;
-    const size_t smem = (size_t)kKC * (Mp + Np) * 8;
-    if (ctx->smem_attr_done.insert((const void*)skinny_khuge_kernel<TM, TN>).second)
-        JUES_CUDA(cudaFuncSetAttribute(skinny_khuge_kernel<TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    skinny_khuge_kernel<TM, TN><<<ctas, 256, smem, ctx->stream>>>(a);
+    const size_t smem = (size_t)2 * kKC * (a.M + a.N) * 8;
+    if (ctx->smem_attr_done.insert((const void*)skinny_khuge_kernel<TM, TN, THREADS>).second)
+        JUES_CUDA(cudaFuncSetAttribute(skinny_khuge_kernel<TM, TN, THREADS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
+    skinny_khuge_kernel<TM, TN, THREADS><<<ctas, THREADS, smem, ctx->stream>>>(a);
     JUES_CUDA(cudaGetLastError());
 }
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 
 bool skinny_gemm(jues_ctx* ctx, const GemmCall& g) {
     static const bool off = getenv("JUES_B200_NO_SKINNY") != nullptr;
     if (off || g.batch != 1 || g.force_cfg >= 0) return false;
+    const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    // ---- matrix-vector: N == 1, A stored K x M (k-contiguous rows) ------------------------------------------
+    if (g.N == 1 && g.transA && g.M >= 256 && g.K >= 64 && g.K <= 8192) {
+        GemvArgs a;
+        a.R = g.M; a.K = (int)g.K;
+        a.L = g.A; a.ldl = g.lda;
+        a.x = g.B; a.sx = g.transB ? g.ldb : 1;       // B is K x 1 (or 1 x K)
+        a.y = g.C; a.sy = 1;
+        a.alpha = g.alpha; a.beta = g.beta;
+        const bool vec = aligned16(g.A) && (g.lda & 1) == 0 && (g.K & 1) == 0;
+        const unsigned grid = (unsigned)std::min<int64_t>((g.M + 7) / 8, (int64_t)sms * 8);
+        const size_t smem = (size_t)g.K * 8;
+        if (ctx->smem_attr_done.insert((const void*)skinny_gemv_kernel<true>).second) {
+            JUES_CUDA(cudaFuncSetAttribute(skinny_gemv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            JUES_CUDA(cudaFuncSetAttribute(skinny_gemv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        }
+        if (vec) skinny_gemv_kernel<true><<<grid, 256, smem, ctx->stream>>>(a);
+        else skinny_gemv_kernel<false><<<grid, 256, smem, ctx->stream>>>(a);
+        JUES_CUDA(cudaGetLastError());
+        ctx->stats.aux_launches += 1;
+        return true;
+    }
+    // ---- matrix-vector: N == 1, A stored M x K (contiguous along the rows) ---------------------------------
+    if (g.N == 1 && !g.transA && g.M >= 2048 && g.K >= 16 && g.K <= 7900) {
+        GemvArgs a;
+        a.R = g.M; a.K = (int)g.K;
+        a.L = g.A; a.ldl = g.lda;
+        a.x = g.B; a.sx = g.transB ? g.ldb : 1;
+        a.y = g.C; a.sy = 1;
+        a.alpha = g.alpha; a.beta = g.beta;
+        if (ctx->smem_attr_done.insert((const void*)skinny_gemv_n_kernel).second)
+            JUES_CUDA(cudaFuncSetAttribute(skinny_gemv_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        skinny_gemv_n_kernel<<<(unsigned)((g.M + 31) / 32), 256, (size_t)(g.K + 256) * 8, ctx->stream>>>(a);
+        JUES_CUDA(cudaGetLastError());
+        ctx->stats.aux_launches += 1;
+        return true;
+    }
+    // ---- K huge, M and N small ('N','T', dense operands) -----------------------------------------------------
     const double M = (double)g.M, N = (double)g.N, K = (double)g.K;
     const double intensity = 2.0 * M * N * K / (8.0 * (M * K + K * N + M * N));
-    // ---- K huge, M and N small ('N','T': both operands contiguous along their small index) -----------------
-    if (!g.transA && g.transB && g.M <= 128 && g.N <= 128 && g.K >= 8192 && intensity < 13.0) {
-        const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    if (!g.transA && g.transB && g.M <= 128 && g.N <= 128 && g.M * g.N <= 4096 && g.K >= 8192 && intensity < 13.0 &&
+        g.lda == g.M && g.ldb == g.N && (g.M & 1) == 0 && (g.N & 1) == 0 && aligned16(g.A) && aligned16(g.B)) {
         int ctas = (int)std::min<int64_t>(2 * sms, (g.K + 4 * kKC - 1) / (4 * kKC));
         KHugeArgs a;
         a.M = (int)g.M; a.N = (int)g.N; a.K = g.K;
         a.kper = ((g.K + ctas - 1) / ctas + kKC - 1) / kKC * kKC;
         ctas = (int)((g.K + a.kper - 1) / a.kper);
-        a.A = g.A; a.lda = g.lda; a.B = g.B; a.ldb = g.ldb;
-        DBuf work(ctx, (size_t)ctas * g.M * g.N);
+        a.A = g.A; a.B = g.B;
+        a.ldz = (ctas + 1) & ~1;
+        DBuf work(ctx, (size_t)a.ldz * g.M * g.N);
         a.W = work.p;
-        const int64_t big = std::max(g.M, g.N), small = std::min(g.M, g.N);
-        if (big <= 32) launch_khuge<2, 2>(ctx, a, ctas);
-        else if (small <= 32) launch_khuge<4, 4>(ctx, a, ctas);
-        else launch_khuge<8, 8>(ctx, a, ctas);
-        ctx->stats.aux_launches += 1;
-        splitk_reduce(ctx, work.p, ctas, g.M, g.N, 1, g.alpha, g.beta, g.C, g.ldc, 0);
-        return true;
-    }
-    if (g.K > 4096 || intensity >= 10.0) return false;
-    // ---- M huge, N small:  C(m, n) = sum_k A(m, k) B(k, n) ---------------------------------------------------
-    if (g.N <= 256 && g.M >= 2048 && g.M >= 16 * g.N) {
-        RowsArgs a;
-        a.R = g.M; a.K = (int)g.K; a.nc = (int)g.N;
-        a.L = g.A; a.ldl = g.lda;
-        a.S = g.B; a.ssk = g.transB ? g.ldb : 1; a.ssc = g.transB ? 1 : g.ldb;
-        a.O = g.C; a.sor = 1; a.soc = g.ldc;
-        a.alpha = g.alpha; a.beta = g.beta;
-        rows_product(ctx, a, g.transA);
-        return true;
-    }
-    // ---- N huge, M small:  C^T(n, m) = sum_k B^T(n, k) A^T(k, m) ------------------------------------------------
-    if (g.M <= 256 && g.N >= 2048 && g.N >= 16 * g.M) {
-        RowsArgs a;
-        a.R = g.N; a.K = (int)g.K; a.nc = (int)g.M;
-        a.L = g.B; a.ldl = g.ldb;
-        a.S = g.A; a.ssk = g.transA ? 1 : g.lda; a.ssc = g.transA ? g.lda : 1;
-        a.O = g.C; a.sor = g.ldc; a.soc = 1;
-        a.alpha = g.alpha; a.beta = g.beta;
-        rows_product(ctx, a, !g.transB);      // B stored K x N: k-contiguous rows of B^T
+        if (std::max(g.M, g.N) <= 32) launch_khuge<2, 2, 256>(ctx, a, ctas);
+        else launch_khuge<4, 4, 256>(ctx, a, ctas);
+        skinny_slices_reduce_kernel<<<(unsigned)((g.M * g.N + 7) / 8), 256, 0, ctx->stream>>>(
+            work.p, a.ldz, ctas, (int)g.M, (int)g.N, g.alpha, g.beta, g.C, g.ldc);
+        JUES_CUDA(cudaGetLastError());
+        ctx->stats.aux_launches += 2;
         return true;
     }
     return false;

@@ -571,6 +571,14 @@ void permute_axpby_strided(jues_ctx* ctx, double alpha, const Ten& in, const int
     const long long total = so;
     if (total == 0) return;
     JUES_REQUIRE(in.p != out.p, "permute: in-place not supported");
+    Timer* tk = nullptr;
+    if (ctx->trace >= 2) {
+        char nm[48];
+        snprintf(nm, sizeof nm, "perm %s>%s %lldx%lldx%lldx%lld%s", ii, io, (long long)in.d[0], (long long)in.d[1],
+                 (long long)in.d[2], (long long)in.d[3], beta != 0.0 ? "+" : "");
+        tk = new Timer(ctx, nm);
+    }
+    struct TkGuard { Timer* t; ~TkGuard() { delete t; } } tkg{tk};
     // merge adjacent output axes that are also adjacent (same order) in the input
     int r = rank;
     for (int q = 0; q + 1 < r;) {

@@ -409,10 +409,11 @@ def test_sampled_elements_of_a_large_generated_transform(ctx):
 
 # ---- the streaming kernels for skinny products (csrc/skinny.cu) ---------------------------------------
 @pytest.mark.parametrize("tA,tB,M,N,K", [
-    ("N", "N", 4100, 20, 100), ("N", "T", 4100, 7, 33), ("T", "N", 3000, 1, 2000), ("T", "T", 2500, 20, 64),
-    ("N", "N", 5000, 100, 20), ("N", "N", 4096, 130, 17), ("T", "N", 2049, 3, 5),
-    ("N", "N", 20, 4100, 100), ("N", "T", 20, 4100, 100), ("T", "N", 3, 5000, 40), ("T", "T", 100, 3000, 20),
-    ("N", "T", 20, 100, 9000), ("N", "T", 20, 20, 10000), ("N", "T", 100, 100, 8200), ("N", "T", 7, 33, 8500)])
+    ("T", "N", 3000, 1, 2000), ("T", "T", 2500, 1, 64), ("T", "N", 257, 1, 4097), ("T", "N", 10000, 1, 200),
+    ("N", "T", 20, 100, 9000), ("N", "T", 20, 20, 10000), ("N", "T", 100, 100, 8200), ("N", "T", 6, 34, 8500),
+    ("N", "T", 128, 128, 8192), ("N", "T", 2, 2, 20001),
+    # shapes next to theirs that stay on the tile kernel
+    ("N", "N", 4100, 20, 100), ("N", "N", 20, 4100, 100), ("T", "N", 3, 5000, 40), ("N", "T", 7, 33, 8500)])
 @pytest.mark.parametrize("beta", [0.0, 0.3])
 def test_gemm_skinny_streaming(ctx, tA, tB, M, N, K, beta):
     rng = np.random.default_rng(M + 7 * N + 13 * K)

@@ -18,16 +18,20 @@ sweeps, cur = [], []
 for k, ms in ph:
     if k == "cc.iteration":
         sweeps.append((ms, cur)); cur = []
-    elif k.startswith("gemm ") or k.startswith("cc.part") or k.startswith("cc.comm"):
+    elif k.startswith("gemm ") or k.startswith("perm ") or k.startswith("cc.part") or k.startswith("cc.comm"):
         cur.append((k, ms))
 ms_sweep, items = sweeps[-1]
 tot = 0.0
+ptot = 0.0
 for k, ms in items:
     if k.startswith("gemm "):
         M, Nn, K, B = (int(x) for x in k.split()[1].split("x"))
         fl = 2.0 * M * Nn * K * B
         tot += ms
         print(f"{ms*1e3:9.1f} us  {fl/ms*1e-9:6.2f} TF/s  {100*ms/ms_sweep:5.1f}%  {k}")
+    elif k.startswith("perm "):
+        ptot += ms
+        print(f"{ms*1e3:9.1f} us  permute          {100*ms/ms_sweep:5.1f}%  {k}")
     else:
         print(f"{ms*1e3:9.1f} us  ------ {k}")
-print(f"sweep {ms_sweep:.3f} ms (traced, eager), gemm sum {tot:.3f} ms")
+print(f"sweep {ms_sweep:.3f} ms (traced, eager), gemm sum {tot:.3f} ms, permute sum {ptot:.3f} ms")
