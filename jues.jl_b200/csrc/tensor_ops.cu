@@ -134,6 +134,7 @@ __global__ void permute_tiled(const double* __restrict__ in, double* __restrict_
     }
 }
 
+
 __global__ void splitk_reduce_kernel(const double* __restrict__ W, int nsplit, long long M, long long N,
                                      long long batch, double alpha, double beta, double* __restrict__ C,
                                      long long ldc, long long strideC) {
