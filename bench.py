@@ -27,8 +27,9 @@ CPU".  One JSON line is printed by rank 0:
   * `cpu_baseline` is the oracle (numpy restatement of the reference's literal algorithm, "port") timed on
     this box's host cores on a bounded sample.
   * `large`: the configurations the metric's targets are quoted on -- RCCSD nbf=300/nocc=60 (fits one GPU:
-    strong scaling over N) and, at N=8, BASELINE config 5 (nbf=460/nocc=60): s/iteration, executed TFLOP/s
-    per GPU, transform time and TFLOP/s, communication ms per sweep.
+    strong scaling over N), the 4-index transform + RMP2 at BASELINE config 4 (nbf=500/nocc=60, strong scaling
+    over N) and, at N=8, BASELINE config 5 (RCCSD nbf=460/nocc=60): s/iteration, executed TFLOP/s per GPU,
+    transform time and TFLOP/s, communication ms per sweep, energies against the same inputs at other rank counts.
   * `next_rows` (extra, N=1 only): AutoRCCSD.do_rccsd with the (T) correction on the same inputs.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port; there is no Julia here) on the
@@ -65,7 +66,7 @@ WEAK_NVIR = {1: 100, 2: 124, 4: 152, 8: 192}   # F_alg(nocc=20, nvir) ~ N * F_al
 SEED = 2024
 REF_MAXIT = 40          # RCCSD.jl:36
 E_TOL = 1e-10           # north_star: correlation energies within 1e-10 Eh
-LARGE = {"strong": (300, 60), "c5": (460, 60)}
+LARGE = {"strong": (300, 60), "c4": (500, 60), "c5": (460, 60)}
 
 
 def _flops():
@@ -395,49 +396,102 @@ def insitu_roofline(ctx, jb, wdev, peak, peak_src, world, nbf):
             "peak_source": peak_src}, comm
 
 
+def large_invariance():
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "large_invariance.json")))
+    except Exception:
+        return {}
+
+
 def large_block(ctx, jb, dist, torch, world, rank, peak):
-    """RCCSD at the shapes the metric's targets are quoted on, storage-less synthetic AO tensor."""
+    """The shapes the metric's targets are quoted on, storage-less synthetic AO tensor: RCCSD nbf=300/nocc=60
+    (strong scaling), RMP2 + transform nbf=500/nocc=60 (BASELINE config 4) and, on 8 GPUs, RCCSD nbf=460/nocc=60
+    (BASELINE config 5).  Energies are compared with the committed values of the same inputs at other rank counts
+    (tests/golden/large_invariance.json: sharding invariance, not an oracle)."""
     res = {}
-    todo = [("strong", *LARGE["strong"])] + ([("c5", *LARGE["c5"])] if world == 8 else [])
-    for tag, nbf, nocc in todo:
+    inv = large_invariance()
+    todo = [("strong", "rccsd", *LARGE["strong"]), ("c4", "rmp2", *LARGE["c4"])] \
+        + ([("c5", "rccsd", *LARGE["c5"])] if world == 8 else [])
+
+    def allmax(vals):
+        if dist is None:
+            return vals
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def allsum(vals):
+        if dist is None:
+            return vals
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    for tag, what, nbf, nocc in todo:
         try:
             v = nbf - nocc
             Cao, Cav, eps = jb.synth.orbitals(nbf, nocc, SEED)
             g = jb.DeviceFourTensor.synth_eri(nbf, seed=SEED, ctx=ctx, virtual=True)
             w = jb.Wfn(nocc, v, eps, Cao, Cav, g)
-            hist = []
-            ctx.set_trace(1)
-            try:
-                jb.RCCSD.do_rccsd(w, ctx=ctx, _maxit=3, _e_hist=hist)
-            finally:
-                ctx.set_trace(0)
-            ph, c = ctx.phases(), ctx.counters()
-            it = [ms for k, ms in ph if k == "cc.iteration"]
-            gf = [ms for k, ms in ph if k == "cc.iteration.gflop"]
-            tr = [ms for k, ms in ph if k == "cc.transform"][0]
-            ms_it = float(np.median(it[1:]))
-            comm_ms = sum(ms for k, ms in ph if k.startswith("cc.comm.")) / len(it)
-            exch_ms = sum(ms for k, ms in ph if k == "tei.exchange")
-            tr_flops = c["gemm_flops"] - sum(gf) * 1e9
-            vals = [ms_it, tr, comm_ms, float(np.median(gf)) * 1e9, tr_flops]
-            if dist is not None:
-                t = torch.tensor(vals[:3], dtype=torch.float64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                s = torch.tensor(vals[3:], dtype=torch.float64, device="cuda")
-                dist.all_reduce(s, op=dist.ReduceOp.SUM)
-                vals = [float(x) for x in t] + [float(x) for x in s]
-            ms_it, tr, comm_ms, fl_it, fl_tr = vals
-            res[tag] = {"workload": f"RCCSD nbf={nbf} nocc={nocc} nvir={v}" + (" (BASELINE config 5)" if tag == "c5" else "")
-                                    + f", generated AO integrals, {world} GPU(s)", "scaling": "strong",
-                        "s_per_iteration": ms_it * 1e-3, "executed_tflops_per_gpu": fl_it / (ms_it * 1e-3) * 1e-12 / world,
-                        "frac_of_fp64_peak_per_gpu": fl_it / (ms_it * 1e-3) * 1e-12 / world / peak,
-                        "transform_s": tr * 1e-3, "transform_tflops_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world,
-                        "transform_frac_of_fp64_peak_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world / peak,
-                        "comm_ms_per_sweep": comm_ms, "transform_exchange_ms_overlapped": exch_ms,
-                        "e_hist": hist, "peak_device_GB": c["bytes_peak"] / 1e9}
+            label = f"nbf={nbf} nocc={nocc} nvir={v}" + {"c4": " (BASELINE config 4)", "c5": " (BASELINE config 5)"}.get(tag, "") \
+                + f", generated AO integrals, {world} GPU(s)"
+            if what == "rmp2":
+                jb.do_rmp2(w, ctx=ctx)                      # warm-up: block cache, kernel variants
+                torch.cuda.synchronize()
+                if dist is not None:
+                    dist.barrier()
+                ctx.set_trace(1)
+                try:
+                    t0 = time.perf_counter()
+                    e = jb.do_rmp2(w, ctx=ctx)
+                    wall = time.perf_counter() - t0
+                finally:
+                    ctx.set_trace(0)
+                ph, c = ctx.phases(), ctx.counters()
+                tr = sum(ms for k, ms in ph if k == "mp2.transform")
+                en = sum(ms for k, ms in ph if k == "mp2.energy")
+                exch = sum(ms for k, ms in ph if k == "tei.exchange")
+                wall, tr, en = allmax([wall, tr, en])
+                (fl_tr,) = allsum([c["gemm_flops"]])
+                ref = inv.get(f"rmp2_nbf{nbf}_nocc{nocc}", {}).get("energy")
+                res[tag] = {"workload": "4-index transform + RMP2 " + label, "scaling": "strong",
+                            "s_per_call": wall, "transform_s": tr * 1e-3, "mp2_energy_ms": en,
+                            "flops_executed": fl_tr, "transform_tflops_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world,
+                            "transform_frac_of_fp64_peak_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world / peak,
+                            "transform_exchange_ms_overlapped": exch, "energy": e,
+                            "abs_dE_vs_other_rank_counts": abs(e - ref) if ref is not None else None,
+                            "peak_device_GB": c["bytes_peak"] / 1e9}
+            else:
+                hist = []
+                ctx.set_trace(1)
+                try:
+                    jb.RCCSD.do_rccsd(w, ctx=ctx, _maxit=3, _e_hist=hist)
+                finally:
+                    ctx.set_trace(0)
+                ph, c = ctx.phases(), ctx.counters()
+                it = [ms for k, ms in ph if k == "cc.iteration"]
+                gf = [ms for k, ms in ph if k == "cc.iteration.gflop"]
+                tr = [ms for k, ms in ph if k == "cc.transform"][0]
+                ms_it = float(np.median(it[1:]))
+                comm_ms = sum(ms for k, ms in ph if k.startswith("cc.comm.")) / len(it)
+                exch_ms = sum(ms for k, ms in ph if k == "tei.exchange")
+                tr_flops = c["gemm_flops"] - sum(gf) * 1e9
+                ms_it, tr, comm_ms = allmax([ms_it, tr, comm_ms])
+                fl_it, fl_tr = allsum([float(np.median(gf)) * 1e9, tr_flops])
+                ref = inv.get(f"rccsd_nbf{nbf}_nocc{nocc}", {}).get("e_hist")
+                d_e = float(np.abs(np.asarray(hist[:len(ref)]) - np.asarray(ref[:len(hist)])).max()) if ref else None
+                res[tag] = {"workload": "RCCSD " + label, "scaling": "strong",
+                            "s_per_iteration": ms_it * 1e-3, "executed_tflops_per_gpu": fl_it / (ms_it * 1e-3) * 1e-12 / world,
+                            "frac_of_fp64_peak_per_gpu": fl_it / (ms_it * 1e-3) * 1e-12 / world / peak,
+                            "transform_s": tr * 1e-3, "transform_tflops_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world,
+                            "transform_frac_of_fp64_peak_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world / peak,
+                            "comm_ms_per_sweep": comm_ms, "transform_exchange_ms_overlapped": exch_ms,
+                            "e_hist": hist, "max_abs_dE_vs_other_rank_counts": d_e,
+                            "peak_device_GB": c["bytes_peak"] / 1e9}
             g.free()
         except Exception as ex:     # noqa: BLE001
             res[tag] = {"error": str(ex)[:300]}
+    res["invariance_reference"] = "tests/golden/large_invariance.json (same inputs at other rank counts / round-1 algorithm; not an oracle)"
     return res
 
 
@@ -630,6 +684,15 @@ def gpu_arm(args, rank, world):
         except Exception as ex:     # noqa: BLE001
             next_rows = {"error": str(ex)[:300]}
     large = run_large()
+    if large:
+        ds = [x for x in ((large.get(t) or {}).get(k) for t in ("strong", "c4", "c5")
+                          for k in ("max_abs_dE_vs_other_rank_counts", "abs_dE_vs_other_rank_counts")) if x is not None]
+        if ds:
+            parity["large_invariance"] = {"max_abs_dE": max(ds), "tol": E_TOL,
+                                          "status": "ok" if max(ds) <= E_TOL else "FAILED",
+                                          "what": "energies of the `large` runs against the same inputs at other rank "
+                                                  "counts / the round-1 algorithm (sharding invariance; not an oracle, "
+                                                  "does not change the exit code)"}
     F_alg, F_ref = fl.rccsd_iter_alg(o, v), fl.rccsd_iter_ref(o, v)
     s_it = ms_step * 1e-3
     h2d = int(g.nbytes // world + Cao.nbytes + Cav.nbytes + eps.nbytes)
@@ -687,7 +750,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the AutoRCCSD(T) extra keys")
-    ap.add_argument("--no-large", action="store_true", help="skip the nbf=300 / config-5 block")
+    ap.add_argument("--no-large", action="store_true", help="skip the nbf=300 / config-4 / config-5 block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
