@@ -144,6 +144,13 @@ struct CC {
     bool sa_ladder = false;
     // static combinations
     DTen Vt, oovo, ooov_t;
+    // OC[a,m,e,f] = 2 <am|ef> - <ma|ef> for f in the slab (one operand for the two singles terms that need both);
+    // ooov_p[i,j,m,b] = <mj|ib>, b in the slab (start value of the o^3 v intermediate contracted with t[m,a])
+    DTen OC, ooov_p;
+    // The sweep with layouts chosen so that no GEMM output needs a permutation pass (batched products over the
+    // slab index, ring products added to H by one kernel, the Fmi term through its (ij)(ab) image).
+    // JUES_B200_PLAIN_SWEEP=1 keeps the one-contraction-per-term form of round 1 (A/B measurements).
+    bool relaid = getenv("JUES_B200_PLAIN_SWEEP") == nullptr;
     // off-diagonal Fock blocks of a non-canonical reference (AutoRCCSD.jl:218-231), zero diagonals,
     // zero padding:  foT[m,i] = f[i,m] (o,o),  fov[m,e] (o,v),  fvv[e,a] (v,v).  fock == false: canonical.
     DTen foT, fov, fvv;
@@ -231,12 +238,19 @@ struct CC {
             ooov_t.alloc(ctx, o, o, o, v);
             axpby(ctx, (size_t)(o * o * o * v), 2.0, ooov.p(), 0.0, ooov_t.p());
             permute_axpby(ctx, -1.0, ooov, "mnie", 1.0, ooov_t, "nmie");
+            if (relaid) {
+                OC.alloc(ctx, v, o, v, vs);
+                permute_axpby(ctx, -1.0, OA, "eamf", 0.0, OC, "amef");
+                axpby(ctx, (size_t)(v * o * v * vs), 2.0, OB.p(), 1.0, OC.p());
+                ooov_p.alloc(ctx, o, o, o, vs);
+                permute_axpby(ctx, 1.0, last_slab(ooov, b0, vs), "mjib", 0.0, ooov_p, "ijmb");
+            }
         }
     }
 
     void register_static() {
         ctx->perm_cache = &pcache;
-        for (DTen* t : {&V, &J, &oooo, &ooov, &Vt, &oovo, &ooov_t, &OA, &OB})
+        for (DTen* t : {&V, &J, &oooo, &ooov, &Vt, &oovo, &ooov_t, &OA, &OB, &OC})
             if (t->p()) pcache.add(t->t, false);
     }
     ~CC() {
@@ -298,11 +312,16 @@ struct CC {
         contract(ctx, 1.0, Vt_S, "mnef", tauh_S, "inef", 0.0, Fmi, "mi");
         contract(ctx, 1.0, V_S, "mnef", tau_S, "ijef", 0.0, Wpp, "mnij");            // 2X
         if (singles) {
-            contract(ctx, 2.0, OB, "amef", tS, "mf", 1.0, FaeT, "ea");
-            contract(ctx, -1.0, OA, "eamf", tS, "mf", 1.0, FaeT, "ea");
             contract(ctx, -1.0, T_S, "mnae", last_slab(ooov_t, b0, vs), "mnie", 0.0, R1, "ia");
-            contract(ctx, 2.0, T_S, "imef", OB, "amef", 1.0, R1, "ia");
-            contract(ctx, -1.0, T_S, "imef", OA, "eamf", 1.0, R1, "ia");
+            if (relaid) {
+                contract(ctx, 1.0, OC, "amef", tS, "mf", 1.0, FaeT, "ea");
+                contract(ctx, 1.0, T_S, "imef", OC, "amef", 1.0, R1, "ia");
+            } else {
+                contract(ctx, 2.0, OB, "amef", tS, "mf", 1.0, FaeT, "ea");
+                contract(ctx, -1.0, OA, "eamf", tS, "mf", 1.0, FaeT, "ea");
+                contract(ctx, 2.0, T_S, "imef", OB, "amef", 1.0, R1, "ia");
+                contract(ctx, -1.0, T_S, "imef", OA, "eamf", 1.0, R1, "ia");
+            }
         } else {
             fill(ctx, R1.p, (size_t)nR1, 0.0);
         }
@@ -354,9 +373,10 @@ struct CC {
             pcache.add(Tp2, true);
             contract(ctx, -0.5, V, "mnef", last_slab(Tp2, b0, vs), "jnfb", 1.0, WJ, "mejb");
             contract(ctx, 0.5, V, "nmef", last_slab(Tp2, b0, vs), "jnfb", 1.0, WE, "mejb");
-            contract(ctx, 1.0, OA, "efmb", t, "jf", 1.0, WJ, "mejb");
+            // for every b of the slab a plain matrix product [(m,e) x f][f x j]: batched, no output permutation
+            contract(ctx, 1.0, OA, "efmb", t, "jf", 1.0, WJ, "mejb", relaid);
             contract(ctx, -1.0, oovo, "mnej", tS, "nb", 1.0, WJ, "mejb");
-            contract(ctx, -1.0, OA, "femb", t, "jf", 1.0, WE, "mejb");
+            contract(ctx, -1.0, OA, "femb", t, "jf", 1.0, WE, "mejb", relaid);
             contract(ctx, 1.0, oovo, "nmej", tS, "nb", 1.0, WE, "mejb");
         } else {
             contract(ctx, -0.5, V, "mnef", T_S, "jnfb", 1.0, WJ, "mejb");
@@ -399,23 +419,45 @@ struct CC {
         contract(ctx, 1.0, Wpp, "mnij", tau_S, "mnab", 0.0, Lhh, "ijab");
         // ---- half residual H for the slab (its (ij)(ab) image is added by residual_finish) ----------
         contract(ctx, 1.0, T, "ijae", last_slab(FaeTt, b0, vs), "eb", 0.0, H, "ijab");
-        contract(ctx, -1.0, T_S, "imab", FmiT, "mj", 1.0, H, "ijab");
-        contract(ctx, 1.0, Tt, "imae", WJ, "mejb", 1.0, H, "ijab");
-        contract(ctx, 1.0, T, "imae", WE, "mejb", 1.0, H, "ijab");
-        contract(ctx, 1.0, T, "mjae", WE, "meib", 1.0, H, "ijab");    // image of T[mibe] WmBEj[maej]
+        if (relaid) {
+            // - T[i,m,a,b] Fmi[m,j] enters through its (ij)(ab) image - Fmi[m,i] T[m,j,a,b] (residual_finish adds
+            // the image of everything in H): [i x m][m x (j,a,b)], no permutation on either side
+            contract(ctx, -1.0, FmiT, "mi", T_S, "mjab", 1.0, H, "ijab");
+            // the three ring products stay in the layouts the GEMM writes ([ia|jb], [ja|ib]); one kernel adds
+            // them to H (three permute-accumulate passes over H before)
+            DTen Ra(ctx, o, v, o, vs), Rb(ctx, o, v, o, vs);
+            contract(ctx, 1.0, Tt, "imae", WJ, "mejb", 0.0, Ra, "iajb");
+            contract(ctx, 1.0, T, "imae", WE, "mejb", 1.0, Ra, "iajb");
+            contract(ctx, 1.0, T, "mjae", WE, "meib", 0.0, Rb, "jaib");   // image of T[mibe] WmBEj[maej]
+            ring_combine(ctx, Ra.p(), Rb.p(), H.p, o, v, vs);
+        } else {
+            contract(ctx, -1.0, T_S, "imab", FmiT, "mj", 1.0, H, "ijab");
+            contract(ctx, 1.0, Tt, "imae", WJ, "mejb", 1.0, H, "ijab");
+            contract(ctx, 1.0, T, "imae", WE, "mejb", 1.0, H, "ijab");
+            contract(ctx, 1.0, T, "mjae", WE, "meib", 1.0, H, "ijab");    // image of T[mibe] WmBEj[maej]
+        }
         if (singles) {
-            DTen Yp(ctx, o, o, o, vs);
-            contract(ctx, 1.0, tauv, "ijef", OA, "efmb", 0.0, Yp, "ijmb");
-            contract(ctx, -1.0, Yp, "ijmb", t, "ma", 1.0, H, "ijab");
-            // rank-1 ring corrections  - t[ie] t[ma] <mb|ej>  - t[ie] t[mb] <am|ej>: contract t[ie] into the
-            // integral first (o^3 v intermediates) instead of building v^3 o ones
-            DTen Q1(ctx, o, o, o, vs), Q2(ctx, o, o, v, o);
-            contract(ctx, 1.0, t, "ie", V_S, "mjeb", 0.0, Q1, "imjb");
-            contract(ctx, -1.0, Q1, "imjb", t, "ma", 1.0, H, "ijab");
+            DTen Yp(ctx, o, o, o, vs), Q2(ctx, o, o, v, o);
+            if (relaid) {
+                // everything that is contracted with t[m,a] over m is summed first:
+                // Yp[i,j,m,b] = <mj|ib> + tau[ijef] <ef|mb> + t[ie] <mj|eb>, then ONE product batched over b
+                axpby(ctx, (size_t)(o * o * o * vs), 1.0, ooov_p.p(), 0.0, Yp.p());
+                contract(ctx, 1.0, tauv, "ijef", OA, "efmb", 1.0, Yp, "ijmb");
+                contract(ctx, 1.0, t, "ie", V_S, "mjeb", 1.0, Yp, "ijmb");
+                contract(ctx, -1.0, Yp, "ijmb", t, "ma", 1.0, H, "ijab", true);
+            } else {
+                contract(ctx, 1.0, tauv, "ijef", OA, "efmb", 0.0, Yp, "ijmb");
+                contract(ctx, -1.0, Yp, "ijmb", t, "ma", 1.0, H, "ijab");
+                // rank-1 ring corrections  - t[ie] t[ma] <mb|ej>  - t[ie] t[mb] <am|ej>: contract t[ie] into the
+                // integral first (o^3 v intermediates) instead of building v^3 o ones
+                DTen Q1(ctx, o, o, o, vs);
+                contract(ctx, 1.0, t, "ie", V_S, "mjeb", 0.0, Q1, "imjb");
+                contract(ctx, -1.0, Q1, "imjb", t, "ma", 1.0, H, "ijab");
+                contract(ctx, -1.0, t, "ma", last_slab(ooov, b0, vs), "mjib", 1.0, H, "ijab");
+            }
             contract(ctx, 1.0, t, "ie", J, "maje", 0.0, Q2, "imaj");
             contract(ctx, -1.0, Q2, "imaj", tS, "mb", 1.0, H, "ijab");
             contract(ctx, 1.0, t, "ie", OB, "ajeb", 1.0, H, "ijab");     // t . <ab|ej>
-            contract(ctx, -1.0, t, "ma", last_slab(ooov, b0, vs), "mjib", 1.0, H, "ijab");
         }
         if (sa_ladder) {
             if (ctx->nranks > 1) JUES_CUDA(cudaStreamWaitEvent(ctx->stream, ev_join, 0));   // ladder blocks have arrived

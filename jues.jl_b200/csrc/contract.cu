@@ -5,6 +5,7 @@
 // hot contractions of the path are laid out so that no permutation is needed).  This plays the
 // role TensorOperations' @tensor / @tensoropt plays in the reference (TTGT).
 #include "contract.h"
+#include "contract_plan.h"
 #include "dgemm.h"
 
 #include <algorithm>
@@ -12,11 +13,6 @@
 namespace jues {
 
 namespace {
-
-struct Grp {
-    std::string s;
-    int64_t n = 1;
-};
 
 int64_t extent_of(char c, const Ten& A, const char* ia, const Ten& B, const char* ib, const Ten& C,
                   const char* ic) {
@@ -31,19 +27,6 @@ int64_t extent_of(char c, const Ten& A, const char* ia, const Ten& B, const char
     };
     chk(A, ia); chk(B, ib); chk(C, ic);
     return e;
-}
-
-// does `idx` equal first+second ?
-bool is_concat(const std::string& idx, const std::string& first, const std::string& second) {
-    return idx == first + second;
-}
-
-// letters of `from` that are in `set`, in the order they appear in `from`
-std::string pick(const char* from, const std::string& set) {
-    std::string r;
-    for (const char* p = from; *p; ++p)
-        if (set.find(*p) != std::string::npos) r.push_back(*p);
-    return r;
 }
 
 // permuted copy of X (axes `ix`) in axis order `tgt`: from the context's PermCache when X is a
@@ -92,112 +75,49 @@ const double* permuted_operand(jues_ctx* ctx, const Ten& X, const char* ix, cons
 }  // namespace
 
 void contract(jues_ctx* ctx, double alpha, const Ten& A, const char* ia, const Ten& B, const char* ib,
-              double beta, const Ten& C, const char* ic) {
+              double beta, const Ten& C, const char* ic, bool batch_last) {
     JUES_REQUIRE((int)strlen(ia) == A.rank && (int)strlen(ib) == B.rank && (int)strlen(ic) == C.rank,
                  "contract: index string length != tensor rank");
-    std::string sa(ia), sb(ib), sc(ic);
-    std::string Mset, Nset, Kset;
-    for (char c : sa) {
-        const bool inB = sb.find(c) != std::string::npos, inC = sc.find(c) != std::string::npos;
-        JUES_REQUIRE(inB != inC, "contract: every index of A must appear in exactly one of B, C");
-        (inC ? Mset : Kset).push_back(c);
+    auto ext = [&](char c) { return extent_of(c, A, ia, B, ib, C, ic); };
+    ContractPlan p;
+    try {
+        p = plan_contraction(ia, ib, ic, ext, batch_last);
+    } catch (const std::invalid_argument& e) {
+        throw Error(JUES_B200_EINVAL, std::string("invalid argument: ") + e.what());
     }
-    for (char c : sb) {
-        const bool inA = sa.find(c) != std::string::npos, inC = sc.find(c) != std::string::npos;
-        JUES_REQUIRE(inA != inC, "contract: every index of B must appear in exactly one of A, C");
-        if (inC) Nset.push_back(c);
-    }
-    JUES_REQUIRE(Mset.size() + Nset.size() == sc.size(), "contract: C has indices found in neither A nor B");
-    JUES_REQUIRE(!Kset.empty(), "contract: no summed index");
-
-    auto ext = [&](const std::string& s) {
-        int64_t n = 1;
-        for (char c : s) n *= extent_of(c, A, ia, B, ib, C, ic);
-        return n;
-    };
-
-    // ---- choose the orders of the M, N and K groups ---------------------------------------------
-    std::string mC = pick(ic, Mset), nC = pick(ic, Nset);
-    bool c_mn = is_concat(sc, mC, nC);  // C = [M..., N...]
-    bool c_nm = is_concat(sc, nC, mC);  // C = [N..., M...]
-    std::string mord, nord;
-    if (c_mn || c_nm) { mord = mC; nord = nC; }
-    else { mord = pick(ia, Mset); nord = pick(ib, Nset); }
-    // K order: prefer the order that leaves the LARGER operand unpermuted
-    const std::string kA = pick(ia, Kset), kB = pick(ib, Kset);
-    auto conforms = [&](const std::string& idx, const std::string& r, const std::string& k) {
-        return is_concat(idx, r, k) || is_concat(idx, k, r);
-    };
-    std::string kord = kA;
-    if (kA != kB) {
-        const bool a_ok_kA = conforms(sa, mord, kA), b_ok_kB = conforms(sb, nord, kB);
-        const bool a_ok_kB = conforms(sa, mord, kB), b_ok_kA = conforms(sb, nord, kA);
-        const int64_t szA = A.size(), szB = B.size();
-        // cost = elements that must be permuted
-        const int64_t cost_kA = (a_ok_kA ? 0 : szA) + (b_ok_kA ? 0 : szB);
-        const int64_t cost_kB = (a_ok_kB ? 0 : szA) + (b_ok_kB ? 0 : szB);
-        kord = cost_kB < cost_kA ? kB : kA;
-    }
-    const int64_t M = ext(mord), N = ext(nord), K = ext(kord);
-
     // ---- operands as matrices ----------------------------------------------------------------------
     DTen tmpA, tmpB, tmpC;
     const double* pa = A.p;
     const double* pb = B.p;
-    bool a_t, b_t;  // BLAS transposition flags
-    // A product with a huge K and small M, N is bandwidth bound: the streaming kernel (skinny.cu) wants both
-    // operands contiguous along their SMALL index, so an operand that must be re-ordered anyway is put there
-    const bool khuge = M <= 128 && N <= 128 && M * N <= 4096 && K >= 8192;
-    if (is_concat(sa, mord, kord)) a_t = false;       // stored M x K
-    else if (is_concat(sa, kord, mord)) a_t = true;   // stored K x M
-    else {
-        // permute into K-contiguous form [K..., M...] (K-huge products: [M..., K...])
-        const std::string tgt = khuge ? mord + kord : kord + mord;
+    if (!p.permA.empty()) {
         int64_t td[4] = {1, 1, 1, 1};
-        for (size_t q = 0; q < tgt.size(); ++q) td[q] = extent_of(tgt[q], A, ia, B, ib, C, ic);
-        pa = permuted_operand(ctx, A, ia, tgt, td, tmpA);
-        a_t = !khuge;
+        for (size_t q = 0; q < p.permA.size(); ++q) td[q] = ext(p.permA[q]);
+        pa = permuted_operand(ctx, A, ia, p.permA, td, tmpA);
     }
-    if (is_concat(sb, kord, nord)) b_t = false;       // stored K x N
-    else if (is_concat(sb, nord, kord)) b_t = true;   // stored N x K
-    else {
-        const std::string tgt = khuge ? nord + kord : kord + nord;
+    if (!p.permB.empty()) {
         int64_t td[4] = {1, 1, 1, 1};
-        for (size_t q = 0; q < tgt.size(); ++q) td[q] = extent_of(tgt[q], A, ia, B, ib, C, ic);
-        pb = permuted_operand(ctx, B, ib, tgt, td, tmpB);
-        b_t = khuge;
+        for (size_t q = 0; q < p.permB.size(); ++q) td[q] = ext(p.permB[q]);
+        pb = permuted_operand(ctx, B, ib, p.permB, td, tmpB);
     }
-
     GemmCall g;
-    g.K = K;
-    g.batch = 1;
-    if (c_mn || (!c_mn && !c_nm)) {
-        // C(M x N) = op(A) op(B)
-        g.transA = a_t; g.transB = b_t;
-        g.M = M; g.N = N;
-        g.A = pa; g.lda = a_t ? K : M;
-        g.B = pb; g.ldb = b_t ? N : K;
-    } else {
-        // C stored [N..., M...]:  C^T(N x M) = op(B)^T op(A)^T
-        g.transA = !b_t; g.transB = !a_t;
-        g.M = N; g.N = M;
-        g.A = pb; g.lda = b_t ? N : K;
-        g.B = pa; g.ldb = a_t ? K : M;
-    }
-    if (c_mn || c_nm) {
-        g.C = C.p; g.ldc = g.M;
+    g.transA = p.transX; g.transB = p.transY;
+    g.M = p.M; g.N = p.N; g.K = p.K; g.batch = p.batch;
+    g.A = p.swapped ? pb : pa; g.lda = p.ldx; g.strideA = p.strideX;
+    g.B = p.swapped ? pa : pb; g.ldb = p.ldy; g.strideB = p.strideY;
+    g.ldc = p.ldc; g.strideC = p.strideC;
+    if (p.tempC.empty()) {
+        g.C = C.p;
         g.alpha = alpha; g.beta = beta;
         dgemm(ctx, g);
     } else {
-        // interleaved output: GEMM into a temporary [M..., N...] and permute-accumulate into C
-        const std::string tgt = mord + nord;
+        // interleaved output: GEMM into a temporary [M..., N...(, batch)] and permute-accumulate into C
         tmpC.buf.alloc(ctx, (size_t)C.size());
         Ten t = C; t.p = tmpC.buf.p;
-        for (size_t q = 0; q < tgt.size(); ++q) t.d[q] = extent_of(tgt[q], A, ia, B, ib, C, ic);
-        g.C = tmpC.buf.p; g.ldc = M;
+        for (size_t q = 0; q < p.tempC.size(); ++q) t.d[q] = ext(p.tempC[q]);
+        g.C = tmpC.buf.p;
         g.alpha = 1.0; g.beta = 0.0;
         dgemm(ctx, g);
-        permute_axpby(ctx, alpha, t, tgt.c_str(), beta, C, ic);
+        permute_axpby(ctx, alpha, t, p.tempC.c_str(), beta, C, ic);
     }
 }
 

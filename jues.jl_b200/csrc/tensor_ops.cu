@@ -179,25 +179,32 @@ __global__ void tau_kernel(const double* __restrict__ T, const double* __restric
 __global__ void amp_combos_kernel(const double* __restrict__ T, const double* __restrict__ t1,
                                   double* __restrict__ Tt, double* __restrict__ tau, double* __restrict__ tauh,
                                   double* __restrict__ Tp2, int o, int v) {
-    extern __shared__ double sh[];  // o x (o+1)
+    extern __shared__ double sh[];  // o x (o+1): sh[j*(o+1)+i] = T[i,j,a,b]
     const long long oo = (long long)o * o;
+    const int half = o >> 1;        // o is even: 16-byte accesses along i
     for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
         const int a = (int)(ab % v), b = (int)(ab / v);
         const long long base = ab * oo;
-        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
-            const int i = e % o, j = e / o;
-            sh[j * (o + 1) + i] = T[base + e];
+        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+            const int i = 2 * (e % half), j = e / half;
+            const double2 x = *reinterpret_cast<const double2*>(T + base + i + (long long)o * j);
+            sh[j * (o + 1) + i] = x.x;
+            sh[j * (o + 1) + i + 1] = x.y;
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
-            const int i = e % o, j = e / o;
-            const double x = sh[j * (o + 1) + i], xt = sh[i * (o + 1) + j];
-            Tt[base + e] = 2.0 * x - xt;
+        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+            const int i = 2 * (e % half), j = e / half;
+            const long long at = base + i + (long long)o * j;
+            const double x0 = sh[j * (o + 1) + i], x1 = sh[j * (o + 1) + i + 1];
+            const double xt0 = sh[i * (o + 1) + j], xt1 = sh[(i + 1) * (o + 1) + j];
+            *reinterpret_cast<double2*>(Tt + at) = make_double2(2.0 * x0 - xt0, 2.0 * x1 - xt1);
             if (t1) {
-                const double tt = t1[i + (long long)o * a] * t1[j + (long long)o * b];
-                tau[base + e] = x + tt;
-                tauh[base + e] = x + 0.5 * tt;
-                Tp2[base + e] = x + 2.0 * tt;
+                const double2 ta = *reinterpret_cast<const double2*>(t1 + i + (long long)o * a);
+                const double tb = t1[j + (long long)o * b];
+                const double tt0 = ta.x * tb, tt1 = ta.y * tb;
+                *reinterpret_cast<double2*>(tau + at) = make_double2(x0 + tt0, x1 + tt1);
+                *reinterpret_cast<double2*>(tauh + at) = make_double2(x0 + 0.5 * tt0, x1 + 0.5 * tt1);
+                *reinterpret_cast<double2*>(Tp2 + at) = make_double2(x0 + 2.0 * tt0, x1 + 2.0 * tt1);
             }
         }
         __syncthreads();
@@ -229,25 +236,62 @@ __global__ void residual_finish_kernel(const double* __restrict__ V, const doubl
                                        const double* __restrict__ Hfull, double* __restrict__ Tn,
                                        const double* __restrict__ eo, const double* __restrict__ ev, int o,
                                        int v, int b0, int vs) {
-    extern __shared__ double sh[];  // o x (o+1)
+    extern __shared__ double sh[];  // o x (o+1): sh[y*(o+1)+x] = H[x,y,b,a]
     const long long oo = (long long)o * o;
+    const int half = o >> 1;        // o is even: 16-byte accesses along i
     for (long long ab = blockIdx.x; ab < (long long)v * vs; ab += gridDim.x) {
         const int a = (int)(ab % v), bl = (int)(ab / v);
         const int b = b0 + bl;
         const long long base = ab * oo;                        // slab-local (a, bl)
         const long long baseT = ((long long)b + (long long)v * a) * oo;  // full (b, a)
-        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
-            const int i = e % o, j = e / o;
-            sh[i * (o + 1) + j] = Hfull[baseT + e];  // sh[i][j] = H[i,j,b,a]
+        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+            const int x = 2 * (e % half), y = e / half;
+            const double2 h = *reinterpret_cast<const double2*>(Hfull + baseT + x + (long long)o * y);
+            sh[y * (o + 1) + x] = h.x;
+            sh[y * (o + 1) + x + 1] = h.y;
         }
         __syncthreads();
         const double dab = -ev[a] - ev[b];
+        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+            const int i = 2 * (e % half), j = e / half;
+            const long long at = base + i + (long long)o * j;
+            const double2 vv = *reinterpret_cast<const double2*>(V + at);
+            const double2 hh = *reinterpret_cast<const double2*>(H + at);
+            double r0 = vv.x + hh.x + sh[i * (o + 1) + j];          // + H[j,i,b,a]
+            double r1 = vv.y + hh.y + sh[(i + 1) * (o + 1) + j];
+            if (L1) { const double2 l = *reinterpret_cast<const double2*>(L1 + at); r0 += l.x; r1 += l.y; }
+            if (L2) { const double2 l = *reinterpret_cast<const double2*>(L2 + at); r0 += l.x; r1 += l.y; }
+            *reinterpret_cast<double2*>(Tn + at) = make_double2(r0 / (eo[i] + eo[j] + dab), r1 / (eo[i + 1] + eo[j] + dab));
+        }
+        __syncthreads();
+    }
+}
+
+// H[i,j,a,b] += R1[i,a,j,b] + R2[j,a,i,b] for the slab (b local): the three particle-hole ring products of a
+// sweep leave the GEMM in their natural layouts ([ia|jb] and [ja|ib]); one pass adds both to the half residual
+// instead of one permute-accumulate pass over H per product.  One block per (a,b): the o x o block of R2 is
+// transposed through shared memory, R1 and H move as 16-byte vectors along i (o is even).
+__global__ void ring_combine_kernel(const double* __restrict__ R1, const double* __restrict__ R2,
+                                    double* __restrict__ H, int o, int v, int vs) {
+    extern __shared__ double sh[];  // o x (o+1): sh[i*(o+1)+j] = R2[j,a,i,b]
+    const long long oo = (long long)o * o, ov = (long long)o * v;
+    const int half = o >> 1;
+    for (long long ab = blockIdx.x; ab < (long long)v * vs; ab += gridDim.x) {
+        const int a = (int)(ab % v), b = (int)(ab / v);
+        const long long rbase = (long long)o * a + ov * o * b;     // [., a, ., b] of an (o,v,o,vs) array
         for (int e = threadIdx.x; e < oo; e += blockDim.x) {
-            const int i = e % o, j = e / o;
-            double r = V[base + e] + H[base + e] + sh[j * (o + 1) + i];  // + H[j,i,b,a]
-            if (L1) r += L1[base + e];
-            if (L2) r += L2[base + e];
-            Tn[base + e] = r / (eo[i] + eo[j] + dab);
+            const int x = e % o, y = e / o;                        // x runs along the contiguous index j of R2
+            sh[y * (o + 1) + x] = R2[rbase + x + ov * y];
+        }
+        __syncthreads();
+        const long long hbase = ab * oo;
+        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+            const int i = 2 * (e % half), j = e / half;
+            const double2 r1 = *reinterpret_cast<const double2*>(R1 + rbase + i + ov * j);
+            double2 h = *reinterpret_cast<double2*>(H + hbase + i + (long long)o * j);
+            h.x += r1.x + sh[i * (o + 1) + j];
+            h.y += r1.y + sh[(i + 1) * (o + 1) + j];
+            *reinterpret_cast<double2*>(H + hbase + i + (long long)o * j) = h;
         }
         __syncthreads();
     }
@@ -283,25 +327,41 @@ __device__ __forceinline__ double block_reduce(double v) {
     return r;  // valid in thread 0
 }
 
-// E = sum V[ijab] (2 X[ijab] - X[jiab]), X = T + t(x)t.  One block per group of (a,b) slabs.
+// E = sum V[ijab] (2 X[ijab] - X[jiab]), X = T + t(x)t.  One block per group of (a,b) slabs; the o x o block
+// of T goes through shared memory (its transposed partner is in the same block), V and T move as 16-byte
+// vectors along i (o is even).
 __global__ void cc_energy_kernel(const double* __restrict__ V, const double* __restrict__ T,
                                  const double* __restrict__ t1, int o, int v, double* __restrict__ partial) {
+    extern __shared__ double sh[];  // o x (o+1): sh[j*(o+1)+i] = T[i,j,a,b]
     const long long oo = (long long)o * o;
+    const int half = o >> 1;
     double acc = 0.0;
     for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
         const int a = (int)(ab % v), b = (int)(ab / v);
         const long long base = ab * oo;
-        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
-            const int i = e % o, j = e / o;
-            double x = T[base + e], xt = T[base + j + (long long)o * i];
-            if (t1) {
-                const double tia = t1[i + (long long)o * a], tjb = t1[j + (long long)o * b];
-                const double tja = t1[j + (long long)o * a], tib = t1[i + (long long)o * b];
-                x += tia * tjb;
-                xt += tja * tib;
-            }
-            acc += V[base + e] * (2.0 * x - xt);
+        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+            const int i = 2 * (e % half), j = e / half;
+            const double2 x = *reinterpret_cast<const double2*>(T + base + i + (long long)o * j);
+            sh[j * (o + 1) + i] = x.x;
+            sh[j * (o + 1) + i + 1] = x.y;
         }
+        __syncthreads();
+        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+            const int i = 2 * (e % half), j = e / half;
+            const double2 vv = *reinterpret_cast<const double2*>(V + base + i + (long long)o * j);
+            double x0 = sh[j * (o + 1) + i], x1 = sh[j * (o + 1) + i + 1];
+            double xt0 = sh[i * (o + 1) + j], xt1 = sh[(i + 1) * (o + 1) + j];
+            if (t1) {
+                const double2 tia = *reinterpret_cast<const double2*>(t1 + i + (long long)o * a);
+                const double2 tib = *reinterpret_cast<const double2*>(t1 + i + (long long)o * b);
+                const double tjb = t1[j + (long long)o * b], tja = t1[j + (long long)o * a];
+                x0 += tia.x * tjb; x1 += tia.y * tjb;
+                xt0 += tja * tib.x; xt1 += tja * tib.y;
+            }
+            acc += vv.x * (2.0 * x0 - xt0);
+            acc += vv.y * (2.0 * x1 - xt1);
+        }
+        __syncthreads();
     }
     const double r = block_reduce<256>(acc);
     if (threadIdx.x == 0) partial[blockIdx.x] = r;
@@ -644,6 +704,7 @@ void amp_combos(jues_ctx* ctx, const double* T, const double* t1, double* Tt, do
                 double* Tp2, int64_t o, int64_t v) {
     const size_t smem = (size_t)o * (o + 1) * sizeof(double);
     JUES_REQUIRE(smem <= 200 * 1024, "amp_combos: nocc too large for the shared-memory block");
+    JUES_REQUIRE((o & 1) == 0, "amp_combos: padded nocc must be even");
     if (ctx->smem_attr_done.insert((const void*)amp_combos_kernel).second)
         JUES_CUDA(cudaFuncSetAttribute(amp_combos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     long long blocks = (long long)v * v;
@@ -666,6 +727,7 @@ void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const dou
                      int64_t v, int64_t b0, int64_t vs) {
     const size_t smem = (size_t)o * (o + 1) * sizeof(double);
     JUES_REQUIRE(smem <= 200 * 1024, "residual_finish: nocc too large for the shared-memory slab");
+    JUES_REQUIRE((o & 1) == 0, "residual_finish: padded nocc must be even");
     if (ctx->smem_attr_done.insert((const void*)residual_finish_kernel).second)
         JUES_CUDA(cudaFuncSetAttribute(residual_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        200 * 1024));
@@ -675,6 +737,20 @@ void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const dou
     if (blocks > cap) blocks = cap;
     residual_finish_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(V, L1, L2, H, Hfull, Tnew, eo, ev,
                                                                          (int)o, (int)v, (int)b0, (int)vs);
+    AUX_LAUNCHED(ctx);
+}
+
+void ring_combine(jues_ctx* ctx, const double* R1, const double* R2, double* H, int64_t o, int64_t v, int64_t vs) {
+    const size_t smem = (size_t)o * (o + 1) * sizeof(double);
+    JUES_REQUIRE((o & 1) == 0, "ring_combine: padded nocc must be even");
+    JUES_REQUIRE(smem <= 200 * 1024, "ring_combine: nocc too large for the shared-memory block");
+    if (ctx->smem_attr_done.insert((const void*)ring_combine_kernel).second)
+        JUES_CUDA(cudaFuncSetAttribute(ring_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long blocks = (long long)v * vs;
+    if (blocks == 0) return;
+    const long long cap = (long long)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    ring_combine_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(R1, R2, H, (int)o, (int)v, (int)vs);
     AUX_LAUNCHED(ctx);
 }
 
@@ -701,10 +777,19 @@ static int reduction_blocks(jues_ctx* ctx, int64_t v) {
     return (int)blocks;
 }
 
+static size_t cc_energy_smem(jues_ctx* ctx, int64_t o) {
+    const size_t smem = (size_t)o * (o + 1) * sizeof(double);
+    JUES_REQUIRE(smem <= 200 * 1024, "cc_energy: nocc too large for the shared-memory block");
+    JUES_REQUIRE((o & 1) == 0, "cc_energy: padded nocc must be even");
+    if (ctx->smem_attr_done.insert((const void*)cc_energy_kernel).second)
+        JUES_CUDA(cudaFuncSetAttribute(cc_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return smem;
+}
+
 void cc_energy_async(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v,
                      double* dev_out) {
     const int blocks = reduction_blocks(ctx, v);
-    cc_energy_kernel<<<blocks, 256, 0, ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
+    cc_energy_kernel<<<blocks, 256, cc_energy_smem(ctx, o), ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
     AUX_LAUNCHED(ctx);
     final_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, blocks, dev_out);
     AUX_LAUNCHED(ctx);
@@ -712,7 +797,7 @@ void cc_energy_async(jues_ctx* ctx, const double* V, const double* T, const doub
 
 double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v) {
     const int blocks = reduction_blocks(ctx, v);
-    cc_energy_kernel<<<blocks, 256, 0, ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
+    cc_energy_kernel<<<blocks, 256, cc_energy_smem(ctx, o), ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
     AUX_LAUNCHED(ctx);
     return finish_reduction(ctx, blocks);
 }

@@ -78,6 +78,9 @@ void divide_Dijab(jues_ctx* ctx, const double* R, double* Tnew, const double* eo
 void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const double* L2, const double* H,
                      const double* Hfull, double* Tnew, const double* eo, const double* ev, int64_t o,
                      int64_t v, int64_t b0, int64_t vs);
+// H[i,j,a,b] += R1[i,a,j,b] + R2[j,a,i,b]: H an (o,o,v,vs) slab, R1 and R2 (o,v,o,vs) -- the ring products in
+// the layouts the GEMM leaves them in, added to the half residual in one pass
+void ring_combine(jues_ctx* ctx, const double* R1, const double* R2, double* H, int64_t o, int64_t v, int64_t vs);
 // tnew[i,a] = R1[i,a] / (eo[i] - ev[a])
 void divide_Dia(jues_ctx* ctx, const double* R1, double* tnew, const double* eo, const double* ev,
                 int64_t o, int64_t v);
