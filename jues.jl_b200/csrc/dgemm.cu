@@ -29,6 +29,9 @@ static const Cfg kCfgs[] = {
     {96, 128, 96, 16, 5, "96x128x16_w96x16_s5", 1.05},
     {80, 128, 80, 16, 6, "80x128x16_w80x16_s6", 1.07},
     {48, 128, 48, 16, 8, "48x128x16_w48x16_s8", 1.20},
+    // narrow tiles for the skinny products of the sweep (N or M = nocc ~ 20: a 64-wide tile is 3x padding)
+    {128, 32, 32, 16, 8, "128x32x16_w32x16_s8", 1.45},
+    {32, 128, 16, 32, 8, "32x128x16_w16x32_s8", 1.45},
 };
 constexpr int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 
@@ -44,7 +47,9 @@ KernelFn kernel_for(int cfg, int* smem) {
         case 4: *smem = SmemLayout<112, 128, 5>::TOTAL; return dgemm_tma_dmma<A_KC, B_KC, 112, 128, 112, 16, 5>;
         case 5: *smem = SmemLayout<96, 128, 5>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 96, 128, 96, 16, 5>;
         case 6: *smem = SmemLayout<80, 128, 6>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 80, 128, 80, 16, 6>;
-        default: *smem = SmemLayout<48, 128, 8>::TOTAL; return dgemm_tma_dmma<A_KC, B_KC, 48, 128, 48, 16, 8>;
+        case 7: *smem = SmemLayout<48, 128, 8>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 48, 128, 48, 16, 8>;
+        case 8: *smem = SmemLayout<128, 32, 8>::TOTAL;  return dgemm_tma_dmma<A_KC, B_KC, 128, 32, 32, 16, 8>;
+        default: *smem = SmemLayout<32, 128, 8>::TOTAL; return dgemm_tma_dmma<A_KC, B_KC, 32, 128, 16, 32, 8>;
     }
 }
 

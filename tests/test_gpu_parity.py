@@ -38,11 +38,14 @@ def test_gemm(ctx, shape, tA, tB):
     assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("cfg", range(8))
+NCFG = 10     # tile configurations of csrc/dgemm.cu (kCfgs)
+
+
+@pytest.mark.parametrize("cfg", range(NCFG))
 @pytest.mark.parametrize("split", [1, 3])
 def test_gemm_every_tile_configuration(ctx, cfg, split, monkeypatch):
     """Force each tile configuration (and split-K) of the DGEMM on ragged shapes, all transposes."""
-    monkeypatch.setenv("JUES_B200_GEMM_CFG", str(cfg + 8 * (split - 1)))
+    monkeypatch.setenv("JUES_B200_GEMM_CFG", str(cfg + NCFG * (split - 1)))
     rng = np.random.default_rng(cfg)
     for (M, N, K) in [(131, 257, 100), (400, 300, 77), (30, 17, 200)]:
         for tA in "NT":
@@ -52,6 +55,11 @@ def test_gemm_every_tile_configuration(ctx, cfg, split, monkeypatch):
                 ref = (A.T if tA == "T" else A) @ (B.T if tB == "T" else B)
                 out = ctx.gemm(tA, tB, 1.0, A, B)
                 assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), (cfg, split, M, N, K, tA, tB)
+                # accumulating epilogue (old values of C fetched in batches)
+                C0 = rng.standard_normal((M, N))
+                out = ctx.gemm(tA, tB, 0.5, A, B, -1.5, C0.copy(order="F"))
+                ref2 = 0.5 * ref - 1.5 * C0
+                assert np.abs(out - ref2).max() <= 1e-12 * max(1.0, np.abs(ref2).max()), (cfg, split, M, N, K, tA, tB, "beta")
 
 
 def test_gemm_skinny_splitk(ctx):

@@ -5,12 +5,14 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import jues.jl_b200 as jb
 ctx = jb.Context(0)
-NCFG = 8
+NCFG = 10
 shapes = [("N", "T", 100, 100, 40000), ("N", "T", 20, 20, 200000), ("T", "N", 400, 400, 10000), ("T", "N", 10000, 1, 2000),
           ("N", "T", 20, 100, 40000), ("N", "T", 20, 100, 200000), ("T", "N", 2000, 1, 2000), ("N", "N", 8000, 20, 100),
           ("N", "N", 200000, 20, 100), ("N", "N", 40000, 100, 20), ("T", "N", 400, 10000, 400), ("N", "N", 40000, 100, 100),
           ("N", "N", 200000, 20, 20), ("T", "N", 400, 2000, 10000), ("N", "N", 20, 40000, 100), ("N", "N", 20, 200000, 100),
-          ("N", "N", 100, 40000, 20)]
+          ("N", "N", 100, 40000, 20), ("T", "N", 20, 200000, 20), ("T", "N", 40000, 100, 20), ("T", "T", 200000, 20, 100)]
+if len(sys.argv) > 1 and sys.argv[1] == "skinny":
+    shapes = [s for s in shapes if min(s[2], s[3]) <= 20 or s[4] <= 20]
 out = []
 for tA, tB, M, N, K in shapes:
     os.environ.pop("JUES_B200_GEMM_CFG", None)
