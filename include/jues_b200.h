@@ -223,6 +223,24 @@ int jues_b200_mrccd_t4(jues_ctx* ctx, const jues_t4* gao,
                        const double* eps, int maxit,
                        double* e_ccd, int* iterations, double* rms_hist, double* e_hist, double* T2_out);
 
+/* ---- density-fitted variants ------------------------------------------ */
+/* MollerPlesset.do_df_rmp2 (src/MollerPlesset/DF-RMP2.jl:1-46) and CoupledCluster.DFRCCD.do_df_rccd
+ * (src/CoupledCluster/DF-RCCD.jl:11-54).  pqP (nao,nao,naux) = (pq|P) and Jpqh (naux,naux) = (P|Q)^(-1/2)
+ * are exactly what DF.setup_df returns (src/Backend/DF.jl:30-51; the reference obtains them from psi4).
+ * b[p,q,Q] = pqP[p,q,P] Jpqh[P,Q] (DF.jl:52-58) is never formed in the AO basis: the orbital coefficients
+ * are contracted first.
+ * df_rmp2: E = sum (ia|jb) (2 (ia|jb) - (ib|ja)) / D with (ia|jb) = b[i,a,Q] b[j,b,Q].
+ * df_rccd: `maxit` sweeps (this driver honours its keyword, DF-RCCD.jl:28) from the MP2 guess (:111-135)
+ * with the integral classes built from b; the ring intermediate WmBeJ follows DF-RCCD.jl:248-258, which
+ * contracts <mn|ef> where RCCD.jl:399-402 contracts <nm|ef>.  e_hist (nullable): [maxit+1]; T2_out
+ * (nullable): (nocc,nocc,nvir,nvir).                                                                */
+int jues_b200_df_rmp2(jues_ctx* ctx, const double* pqP, int64_t nao, int64_t naux, const double* Jpqh,
+                      const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                      const double* eps, double* e_mp2);
+int jues_b200_df_rccd(jues_ctx* ctx, const double* pqP, int64_t nao, int64_t naux, const double* Jpqh,
+                      const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                      const double* eps, int maxit, double* e_ccd, double* e_hist, double* T2_out);
+
 /* ---- instrumentation (bench.py) ---------------------------------------------------------- */
 /* Statistics of the last entry-point call on this context: CUDA-event milliseconds per phase
  * on the library's stream, FP64 flops issued by the GEMM kernels, kernel launch counts.

@@ -41,7 +41,7 @@ from . import _lib
 from ._lib import LibraryMissing  # noqa: F401
 
 __all__ = ["Wfn", "Context", "DeviceFourTensor", "tei_transform", "get_eri", "do_rmp2", "RCCD",
-           "RCCSD", "AutoRCCSD", "mRCCD", "get_fock", "compute_pT", "CC_DEFAULTS", "gemm", "JuesError", "LibraryMissing", "default_context", "synth"]
+           "RCCSD", "AutoRCCSD", "mRCCD", "DF", "DFRCCD", "do_df_rmp2", "get_fock", "compute_pT", "CC_DEFAULTS", "gemm", "JuesError", "LibraryMissing", "default_context", "synth"]
 
 ERROR_NAMES = {-1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENCCL", -5: "ESTATE"}
 
@@ -86,6 +86,9 @@ class Wfn:
     hao: Optional[np.ndarray] = None      # (nbf, nbf) core Hamiltonian
     Ca: Optional[np.ndarray] = None       # (nbf, nmo) all MO coefficients; default [Cao Cav]
     energy: float = 0.0                   # reference energy (only printed by the reference)
+    # density fitting: (pqP, Jpqh) exactly as DF.setup_df returns them (DF.jl:30-51).  The reference asks psi4
+    # for them; psi4 is not assumed here, so whoever builds the Wfn supplies them.
+    df: Optional[tuple] = None
 
     def __post_init__(self):
         if self.nbeta < 0:
@@ -698,6 +701,77 @@ class _mRCCD:
 
 
 mRCCD = _mRCCD()
+
+
+# ------------------------------------------------------------------------------------------
+# Density fitting: DF.setup_df, MollerPlesset.do_df_rmp2, CoupledCluster.DFRCCD.do_df_rccd
+# ------------------------------------------------------------------------------------------
+class _DF:
+    """JuES.DF"""
+
+    @staticmethod
+    def setup_df(refWfn: Wfn, dfbname: str = "default"):
+        """DF.setup_df (DF.jl:30-51) returns (pqP, Jpqh) = ((pq|P), (P|Q)^(-1/2)) from psi4; here they are the
+        `df` field of the Wfn (dfbname is accepted for the call signature and has nothing to select)."""
+        if refWfn.df is None:
+            raise JuesError(-1, "setup_df: this Wfn carries no density-fitting tensors (Wfn.df = (pqP, Jpqh))")
+        pqP, Jpqh = refWfn.df
+        return pqP, Jpqh
+
+
+DF = _DF()
+
+
+def _df_args(refWfn: Wfn, dfbname: str):
+    pqP, Jpqh = DF.setup_df(refWfn, dfbname)
+    o, v = int(refWfn.nalpha), int(refWfn.nvira)
+    nao = np.asarray(refWfn.Cao).shape[0]
+    pqP = _f(pqP)
+    if pqP.ndim != 3 or pqP.shape[0] != nao or pqP.shape[1] != nao:
+        raise JuesError(-1, f"pqP must be (nao, nao, naux) with nao = {nao}")
+    naux = pqP.shape[2]
+    Jpqh = _f(Jpqh, (naux, naux))
+    Cao = _f(refWfn.Cao, (nao, o))
+    Cav = _f(refWfn.Cav, (nao, v))
+    eps = _f(refWfn.epsa)
+    if eps.shape[0] < o + v:
+        raise JuesError(-1, "epsa shorter than nalpha + nvira")
+    return pqP, nao, naux, Jpqh, Cao, o, Cav, v, eps
+
+
+def do_df_rmp2(refWfn: Wfn, ctx: Optional[Context] = None, *, dfbname: str = "default") -> float:
+    """MollerPlesset.do_df_rmp2(refWfn) (DF-RMP2.jl:1-46)."""
+    pqP, nao, naux, Jpqh, Cao, o, Cav, v, eps = _df_args(refWfn, dfbname)
+    ctx = ctx or default_context()
+    e = C.c_double()
+    ctx._check(ctx._lib.jues_b200_df_rmp2(ctx._h, _p(pqP), nao, naux, _p(Jpqh), _p(Cao), o, _p(Cav), v, _p(eps),
+                                          C.byref(e)))
+    return e.value
+
+
+class _DFRCCD:
+    """JuES.CoupledCluster.DFRCCD"""
+
+    def do_df_rccd(self, refWfn: Wfn, ctx: Optional[Context] = None, *, maxit: int = 40, doprint: bool = False,
+                   return_T2: bool = False, dfbname: str = "default", _e_hist: Optional[list] = None):
+        """DFRCCD.do_df_rccd(refWfn; maxit=40, doprint=false, return_T2=false, dfbname="default")
+        (DF-RCCD.jl:11-54): `maxit` sweeps from the MP2 guess.  Returns the correlation energy, or
+        (energy, T2) with return_T2."""
+        pqP, nao, naux, Jpqh, Cao, o, Cav, v, eps = _df_args(refWfn, dfbname)
+        ctx = ctx or default_context()
+        maxit = int(maxit)
+        e = C.c_double()
+        hist = np.zeros(maxit + 1)
+        T2 = np.empty((o, o, v, v), order="F") if return_T2 else None
+        ctx._cb_shapes(o, v)
+        ctx._check(ctx._lib.jues_b200_df_rccd(ctx._h, _p(pqP), nao, naux, _p(Jpqh), _p(Cao), o, _p(Cav), v, _p(eps),
+                                              maxit, C.byref(e), _p(hist), _p(T2)))
+        if _e_hist is not None:
+            _e_hist[:] = list(hist)
+        return (e.value, T2) if return_T2 else e.value
+
+
+DFRCCD = _DFRCCD()
 
 
 def compute_pT(*, T1, T2, Vvvvo, Vvooo, Vvovo, fo, fv, ctx: Optional[Context] = None) -> float:

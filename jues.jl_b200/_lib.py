@@ -94,6 +94,10 @@ SIGNATURES = {
     "jues_b200_mrccd_t4": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int64, c_double_p,
                                      C.c_int64, c_double_p, C.c_int, c_double_p, c_int_p, c_double_p,
                                      c_double_p, c_double_p]),
+    "jues_b200_df_rmp2": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int64, c_double_p, c_double_p, C.c_int64,
+                                    c_double_p, C.c_int64, c_double_p, c_double_p]),
+    "jues_b200_df_rccd": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, C.c_int64, c_double_p, c_double_p, C.c_int64,
+                                    c_double_p, C.c_int64, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p]),
     "jues_b200_sa_ladder": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, C.c_int64, C.c_int,
                                       c_double_p]),
     "jues_b200_init_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),

@@ -820,6 +820,49 @@ extern "C" int jues_b200_mrccd_t4(jues_ctx* ctx, const jues_t4* gao, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Density-fitted variants (DF-RMP2.jl:1-46, DF-RCCD.jl:11-54)
+// ---------------------------------------------------------------------------------------------
+extern "C" int jues_b200_df_rmp2(jues_ctx* ctx, const double* pqP, int64_t nao, int64_t naux, const double* Jpqh,
+                                 const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                                 const double* eps, double* e_mp2) {
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            return jues_b200_df_rmp2(m, pqP, nao, naux, Jpqh, Cao, nocc, Cav, nvir, eps, lead ? e_mp2 : &e_);
+        });
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    JUES_REQUIRE(e_mp2 != nullptr, "null energy output");
+    Timer total(ctx, "total");
+    Problem P;
+    setup_problem(ctx, P, nao, Cao, nocc, Cav, nvir, eps);
+    *e_mp2 = df_rmp2_dev(ctx, P, pqP, naux, Jpqh);
+    JUES_API_END(ctx)
+}
+
+extern "C" int jues_b200_df_rccd(jues_ctx* ctx, const double* pqP, int64_t nao, int64_t naux, const double* Jpqh,
+                                 const double* Cao, int64_t nocc, const double* Cav, int64_t nvir,
+                                 const double* eps, int maxit, double* e_ccd, double* e_hist, double* T2_out) {
+    if (is_group_call(ctx))
+        return group_run(ctx, [&](jues_ctx* m, bool lead) {
+            double e_;
+            return jues_b200_df_rccd(m, pqP, nao, naux, Jpqh, Cao, nocc, Cav, nvir, eps, maxit, lead ? e_ccd : &e_,
+                                     lead ? e_hist : nullptr, lead ? T2_out : nullptr);
+        });
+    JUES_API_BEGIN(ctx)
+    begin_call(ctx);
+    JUES_REQUIRE(e_ccd != nullptr, "null energy output");
+    Timer total(ctx, "total");
+    Problem P;
+    setup_problem(ctx, P, nao, Cao, nocc, Cav, nvir, eps);
+    CCResult r = df_rccd_dev(ctx, P, pqP, naux, Jpqh, maxit, T2_out, ctx->amp_cb, ctx->amp_user);
+    *e_ccd = r.energy;
+    if (e_hist)
+        for (int k = 0; k <= maxit; ++k) e_hist[k] = r.e_hist[k];
+    JUES_API_END(ctx)
+}
+
+// ---------------------------------------------------------------------------------------------
 // Kernel-level check of the packed (symmetric / antisymmetric) particle-particle ladder
 // ---------------------------------------------------------------------------------------------
 #include "dgemm.h"

@@ -147,10 +147,15 @@ struct CC {
     // OC[a,m,e,f] = 2 <am|ef> - <ma|ef> for f in the slab (one operand for the two singles terms that need both);
     // ooov_p[i,j,m,b] = <mj|ib>, b in the slab (start value of the o^3 v intermediate contracted with t[m,a])
     DTen OC, ooov_p;
+    // Vx[m,e,j,b] = <mj|eb>, b in the slab: start value of the ring intermediate WJ
+    DTen Vx;
     // The sweep with layouts chosen so that no GEMM output needs a permutation pass (batched products over the
     // slab index, ring products added to H by one kernel, the Fmi term through its (ij)(ab) image).
     // JUES_B200_PLAIN_SWEEP=1 keeps the one-contraction-per-term form of round 1 (A/B measurements).
     bool relaid = getenv("JUES_B200_PLAIN_SWEEP") == nullptr;
+    // DF-RCCD.jl:256 contracts <mn|ef> where RCCD.jl:402 contracts <nm|ef> in the third term of WmBeJ, i.e. its
+    // ring intermediate is <mb|ej> + 1/2 <mn|ef> (T[njfb] - T[jnfb]): the density-fitted driver follows its file
+    bool df_wmbej = false;
     // off-diagonal Fock blocks of a non-canonical reference (AutoRCCSD.jl:218-231), zero diagonals,
     // zero padding:  foT[m,i] = f[i,m] (o,o),  fov[m,e] (o,v),  fvv[e,a] (v,v).  fock == false: canonical.
     DTen foT, fov, fvv;
@@ -218,6 +223,12 @@ struct CC {
                 extract(M, nmo, nsl, o, 0, o, os, OB.p(), v, o, v, vs);                        // <aj|eb>
             }
         }
+        build_static();
+    }
+
+    // packed ladder operand and the static combinations of the classes (shared by the transform and the
+    // density-fitted builds)
+    void build_static() {
         Timer t(ctx, "cc.static");
         if (getenv("JUES_B200_PLAIN_LADDER") == nullptr) {
             sa_ld = round_up(sa_pairs(v), 2);
@@ -232,6 +243,10 @@ struct CC {
         Vt.alloc(ctx, o, o, v, v);
         axpby(ctx, n2, 2.0, V.p(), 0.0, Vt.p());
         permute_axpby(ctx, -1.0, V, "ijab", 1.0, Vt, "jiab");          // Vt = 2V - V(ji)
+        if (relaid) {
+            Vx.alloc(ctx, o, v, o, vs);
+            permute_axpby(ctx, 1.0, last_slab(V, b0, vs), "mjeb", 0.0, Vx, "mejb");
+        }
         if (singles) {
             oovo.alloc(ctx, o, o, v, o);
             permute_axpby(ctx, 1.0, ooov, "nmje", 0.0, oovo, "mnej");   // <mn|ej> = <nm|je>
@@ -246,6 +261,31 @@ struct CC {
                 permute_axpby(ctx, 1.0, last_slab(ooov, b0, vs), "mjib", 0.0, ooov_p, "ijmb");
             }
         }
+    }
+
+    // The integral classes of RCCD from three-index tensors (DF-RCCD.jl:77-89 and the products its sweep
+    // forms from them): bov[i,a,Q], boo[i,j,Q], bvv[a,b,Q] on the device, Q padded to nx.
+    //   <ij|ab> = bov[i,a,Q] bov[j,b,Q]      <me|jb> = boo[m,j,Q] bvv[e,b,Q]
+    //   <mn|ij> = boo[m,i,Q] boo[n,j,Q]      <ef|ab> = bvv[e,a,Q] bvv[f,b,Q]   (b in this rank's slab)
+    // The o^2 v^2-sized classes are formed on every rank (o^2 v^2 naux flops), <vv|vv> only for the slab.
+    void build_integrals_df(const Ten& bov, const Ten& boo, const Ten& bvv) {
+        JUES_REQUIRE(!singles, "the density-fitted classes are those of RCCD");
+        {
+            Timer t(ctx, "cc.transform");
+            const int64_t nx = bov.d[2];
+            V.alloc(ctx, o, o, v, v);
+            contract(ctx, 1.0, bov, "iaQ", bov, "jbQ", 0.0, V, "ijab");
+            J.alloc(ctx, o, v, o, v);
+            contract(ctx, 1.0, boo, "mjQ", bvv, "ebQ", 0.0, J, "mejb");
+            oooo.alloc(ctx, o, o, o, o);
+            contract(ctx, 1.0, boo, "miQ", boo, "njQ", 0.0, oooo, "mnij");
+            DTen bvvS(ctx, v, vs, nx);
+            const int64_t sd[4] = {v, v, nx, 1}, dd[4] = {v, vs, nx, 1}, ext[4] = {v, vs, nx, 1};
+            block_copy(ctx, bvv.p + v * b0, sd, bvvS.p(), dd, ext);
+            W4.alloc(ctx, v, v, v, vs);
+            contract(ctx, 1.0, bvv, "eaQ", bvvS, "fbQ", 0.0, W4, "efab");
+        }
+        build_static();
     }
 
     void register_static() {
@@ -365,14 +405,21 @@ struct CC {
         TraceTimer* tr_ring = new TraceTimer(ctx, "cc.part.ringW");
         const size_t ns = (size_t)(o * o * v * vs);
         DTen WJ(ctx, o, v, o, vs), WE(ctx, o, v, o, vs);
-        permute_axpby(ctx, 1.0, V_S, "mjeb", 0.0, WJ, "mejb");                       // <mb|ej> = <mj|eb>
-        axpby(ctx, ns, -1.0, J_S.p, 0.0, WE.p());                                      // -<mb|je> = -(mj|eb)
-        contract(ctx, 0.5, Vt, "mnef", T_S, "njfb", 1.0, WJ, "mejb");
+        // WJ starts from <mb|ej> = <mj|eb>, WE from -<mb|je> = -(mj|eb): read by the epilogue of the first
+        // product into each (Cin), not copied first
+        if (relaid) {
+            contract(ctx, 0.5, df_wmbej ? V : Vt, "mnef", T_S, "njfb", 1.0, WJ, "mejb", false, Vx.p());
+        } else {
+            permute_axpby(ctx, 1.0, V_S, "mjeb", 0.0, WJ, "mejb");
+            axpby(ctx, ns, -1.0, J_S.p, 0.0, WE.p());
+            contract(ctx, 0.5, df_wmbej ? V : Vt, "mnef", T_S, "njfb", 1.0, WJ, "mejb");
+        }
         if (singles) {
             // T/2 + tt = (T + 2 tt) / 2: one operand serves both rings
             pcache.add(Tp2, true);
             contract(ctx, -0.5, V, "mnef", last_slab(Tp2, b0, vs), "jnfb", 1.0, WJ, "mejb");
-            contract(ctx, 0.5, V, "nmef", last_slab(Tp2, b0, vs), "jnfb", 1.0, WE, "mejb");
+            if (relaid) contract(ctx, 0.5, V, "nmef", last_slab(Tp2, b0, vs), "jnfb", -1.0, WE, "mejb", false, J_S.p);
+            else contract(ctx, 0.5, V, "nmef", last_slab(Tp2, b0, vs), "jnfb", 1.0, WE, "mejb");
             // for every b of the slab a plain matrix product [(m,e) x f][f x j]: batched, no output permutation
             contract(ctx, 1.0, OA, "efmb", t, "jf", 1.0, WJ, "mejb", relaid);
             contract(ctx, -1.0, oovo, "mnej", tS, "nb", 1.0, WJ, "mejb");
@@ -380,7 +427,8 @@ struct CC {
             contract(ctx, 1.0, oovo, "nmej", tS, "nb", 1.0, WE, "mejb");
         } else {
             contract(ctx, -0.5, V, "mnef", T_S, "jnfb", 1.0, WJ, "mejb");
-            contract(ctx, 0.5, V, "nmef", T_S, "jnfb", 1.0, WE, "mejb");
+            if (relaid) contract(ctx, 0.5, V, "nmef", T_S, "jnfb", -1.0, WE, "mejb", false, J_S.p);
+            else contract(ctx, 0.5, V, "nmef", T_S, "jnfb", 1.0, WE, "mejb");
         }
         delete tr_ring;
         // ---- ladders ---------------------------------------------------------------------------------
@@ -671,11 +719,99 @@ struct CC {
 
 }  // namespace
 
+static CCResult cc_run(jues_ctx* ctx, Problem& P, CC& cc, bool singles, int maxit, int guess_mode, double* T1_out,
+                       double* T2_out, jues_b200_amp_cb cb, void* cb_user);
+
 CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int maxit, int guess_mode,
                 double* T1_out, double* T2_out, jues_b200_amp_cb cb, void* cb_user) {
     JUES_REQUIRE(maxit >= 0, "maxit must be non-negative");
     CC cc(ctx, P, singles);
     cc.build_integrals(gao);
+    return cc_run(ctx, P, cc, singles, maxit, guess_mode, T1_out, T2_out, cb, cb_user);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Density fitting (DF.jl:52-58, DF-RMP2.jl:1-46, DF-RCCD.jl:11-89)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// b[p,q,Q] = C1[mu,p] C2[nu,q] pqP[mu,nu,P] Jpqh[P,Q] for the orbital blocks the caller asks for.  The
+// reference multiplies by Jpqh first (N^2 naux^2); here the orbital coefficients go first (the same sums in
+// a cheaper order: o N^2 naux + ... + o v naux^2).
+struct DFTensors {
+    DTen bov, boo, bvv;
+    int64_t nx = 0;
+};
+
+void df_tensors(jues_ctx* ctx, Problem& P, const double* pqP, int64_t naux, const double* Jpqh, bool all_blocks,
+                DFTensors& B) {
+    JUES_REQUIRE(pqP && Jpqh, "density fitting: null pqP / Jpqh");
+    JUES_REQUIRE(naux > 0, "density fitting: naux must be positive");
+    const int64_t n = P.nao, np = P.np, o = P.o, v = P.v, nx = round_up(naux, 2);
+    B.nx = nx;
+    DTen pq(ctx, np, np, nx), Jh(ctx, nx, nx);
+    pq.buf.zero(); Jh.buf.zero();
+    for (int64_t q = 0; q < naux; ++q)       // one (nao x nao) plane per auxiliary function into the padded block
+        JUES_CUDA(cudaMemcpy2DAsync(pq.p() + np * np * q, (size_t)np * 8, pqP + n * n * q, (size_t)n * 8, (size_t)n * 8,
+                                    (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    JUES_CUDA(cudaMemcpy2DAsync(Jh.p(), (size_t)nx * 8, Jpqh, (size_t)naux * 8, (size_t)naux * 8, (size_t)naux,
+                                cudaMemcpyHostToDevice, ctx->stream));
+    JUES_CUDA(cudaStreamSynchronize(ctx->stream));     // the caller's arrays are not retained
+    const Ten Co(P.Co.p, np, o), Cv(P.Cv.p, np, v);
+    DTen X1(ctx, o, np, nx);
+    contract(ctx, 1.0, Co, "mi", pq, "mnP", 0.0, X1, "inP");
+    {
+        DTen Y(ctx, o, v, nx);
+        contract(ctx, 1.0, X1, "inP", Cv, "na", 0.0, Y, "iaP", true);
+        B.bov.alloc(ctx, o, v, nx);
+        contract(ctx, 1.0, Y, "iaP", Jh, "PQ", 0.0, B.bov, "iaQ");
+    }
+    if (!all_blocks) return;
+    {
+        DTen Y(ctx, o, o, nx);
+        contract(ctx, 1.0, X1, "inP", Co, "nj", 0.0, Y, "ijP", true);
+        B.boo.alloc(ctx, o, o, nx);
+        contract(ctx, 1.0, Y, "ijP", Jh, "PQ", 0.0, B.boo, "ijQ");
+    }
+    X1.release();
+    DTen X2(ctx, v, np, nx), Y(ctx, v, v, nx);
+    contract(ctx, 1.0, Cv, "ma", pq, "mnP", 0.0, X2, "anP");
+    contract(ctx, 1.0, X2, "anP", Cv, "nb", 0.0, Y, "abP", true);
+    B.bvv.alloc(ctx, v, v, nx);
+    contract(ctx, 1.0, Y, "abP", Jh, "PQ", 0.0, B.bvv, "abQ");
+}
+
+}  // namespace
+
+double df_rmp2_dev(jues_ctx* ctx, Problem& P, const double* pqP, int64_t naux, const double* Jpqh) {
+    const int64_t o = P.o, v = P.v;
+    DFTensors B;
+    DTen ijab(ctx, o, o, v, v);
+    {
+        Timer t(ctx, "mp2.transform");
+        df_tensors(ctx, P, pqP, naux, Jpqh, false, B);
+        contract(ctx, 1.0, B.bov, "iaQ", B.bov, "jbQ", 0.0, ijab, "ijab");     // (ia|jb), DF-RMP2.jl:33-35
+    }
+    // every rank of a multi-GPU context forms the whole (small) sum: no exchange
+    Timer t(ctx, "mp2.energy");
+    return mp2_energy(ctx, ijab.p(), P.eo.p, P.ev.p, o, v, 0, v);
+}
+
+CCResult df_rccd_dev(jues_ctx* ctx, Problem& P, const double* pqP, int64_t naux, const double* Jpqh, int maxit,
+                     double* T2_out, jues_b200_amp_cb cb, void* cb_user) {
+    JUES_REQUIRE(maxit >= 0, "maxit must be non-negative");
+    CC cc(ctx, P, false);
+    cc.df_wmbej = true;
+    {
+        DFTensors B;
+        df_tensors(ctx, P, pqP, naux, Jpqh, true, B);
+        cc.build_integrals_df(B.bov, B.boo, B.bvv);
+    }
+    return cc_run(ctx, P, cc, false, maxit, 1, nullptr, T2_out, cb, cb_user);   // T2_init!: the MP2 guess (:111-135)
+}
+
+static CCResult cc_run(jues_ctx* ctx, Problem& P, CC& cc, bool singles, int maxit, int guess_mode, double* T1_out,
+                       double* T2_out, jues_b200_amp_cb cb, void* cb_user) {
     cc.register_static();
     cc.guess(guess_mode);
     if (!cb) cc.allow_graphs(maxit);

@@ -30,6 +30,13 @@ double rmp2_dev(jues_ctx* ctx, Problem& P, GaoSource& gao);
 CCResult cc_dev(jues_ctx* ctx, Problem& P, GaoSource& gao, bool singles, int maxit, int guess_mode,
                 double* T1_out, double* T2_out, jues_b200_amp_cb cb, void* cb_user);
 
+// Density-fitted variants.  pqP (nao,nao,naux) = (pq|P) and Jpqh (naux,naux) = (P|Q)^(-1/2) are HOST arrays, what
+// DF.setup_df returns (DF.jl:30-51).  do_df_rmp2 (DF-RMP2.jl:1-46); do_df_rccd (DF-RCCD.jl:11-54): `maxit` sweeps
+// from the MP2 guess with the density-fitted file's own ring intermediate (DF-RCCD.jl:248-258).
+double df_rmp2_dev(jues_ctx* ctx, Problem& P, const double* pqP, int64_t naux, const double* Jpqh);
+CCResult df_rccd_dev(jues_ctx* ctx, Problem& P, const double* pqP, int64_t naux, const double* Jpqh, int maxit,
+                     double* T2_out, jues_b200_amp_cb cb, void* cb_user);
+
 // AutoRCCSD.do_rccsd (AutoRCCSD.jl:193-301; options CoupledCluster.jl:36-43)
 struct AutoOptions {
     int max_iter = 50;

@@ -75,7 +75,7 @@ const double* permuted_operand(jues_ctx* ctx, const Ten& X, const char* ix, cons
 }  // namespace
 
 void contract(jues_ctx* ctx, double alpha, const Ten& A, const char* ia, const Ten& B, const char* ib,
-              double beta, const Ten& C, const char* ic, bool batch_last) {
+              double beta, const Ten& C, const char* ic, bool batch_last, const double* Cin) {
     JUES_REQUIRE((int)strlen(ia) == A.rank && (int)strlen(ib) == B.rank && (int)strlen(ic) == C.rank,
                  "contract: index string length != tensor rank");
     auto ext = [&](char c) { return extent_of(c, A, ia, B, ib, C, ic); };
@@ -105,9 +105,11 @@ void contract(jues_ctx* ctx, double alpha, const Ten& A, const char* ia, const T
     g.A = p.swapped ? pb : pa; g.lda = p.ldx; g.strideA = p.strideX;
     g.B = p.swapped ? pa : pb; g.ldb = p.ldy; g.strideB = p.strideY;
     g.ldc = p.ldc; g.strideC = p.strideC;
+    JUES_REQUIRE(Cin == nullptr || p.tempC.empty(), "contract: Cin with an interleaved output");
     if (p.tempC.empty()) {
         g.C = C.p;
         g.alpha = alpha; g.beta = beta;
+        g.Cin = Cin;
         dgemm(ctx, g);
     } else {
         // interleaved output: GEMM into a temporary [M..., N...(, batch)] and permute-accumulate into C

@@ -29,6 +29,8 @@ struct PermCache {
 // C[ic] = alpha * sum_{shared letters} A[ia] * B[ib] + beta * C[ic]
 // batch_last: the last letter of ic (also the last letter of ia and/or ib) is a batch index -- one batched
 // GEMM launch instead of a GEMM with an interleaved output and a permutation pass (contract_plan.h)
+// Cin: beta multiplies Cin (a tensor with the layout of C) instead of C -- a product that starts from a static
+// tensor needs no copy pass (only for contractions whose output needs no permutation)
 void contract(jues_ctx* ctx, double alpha, const Ten& A, const char* ia, const Ten& B, const char* ib,
-              double beta, const Ten& C, const char* ic, bool batch_last = false);
+              double beta, const Ten& C, const char* ic, bool batch_last = false, const double* Cin = nullptr);
 }  // namespace jues

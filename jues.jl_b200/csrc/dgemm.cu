@@ -100,7 +100,8 @@ void choose_cfg(jues_ctx* ctx, int64_t M, int64_t N, int64_t K, int64_t batch, b
                              (double)((N + kCfgs[c].BN - 1) / kCfgs[c].BN) * (double)batch;
         const double area = (double)kCfgs[c].BM * kCfgs[c].BN;
         int max_split = 1;
-        if (allow_split && tiles < sms) max_split = (int)std::min<double>(64.0, std::max(1.0, KT / 8.0));
+        // (a product of one or two tiles may split 128-way: one CTA per SM)
+        if (allow_split && tiles < sms) max_split = (int)std::min<double>(tiles * 64 <= sms ? 128.0 : 64.0, std::max(1.0, KT / 8.0));
         for (int sp = 1; sp <= max_split; sp = sp < 4 ? sp + 1 : sp * 2) {
             const int ktp = (KT + sp - 1) / sp;
             const double waves = ceil(tiles * sp / sms);
@@ -189,11 +190,12 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
         work.alloc(ctx, (size_t)g.M * g.N * ksplit * g.batch);
         p.C = work.p; p.ldc = g.M; p.strideSplit = g.M * g.N; p.strideC = g.M * g.N * ksplit;
         p.alpha = 1.0; p.beta = 0.0;
+        p.Cin = nullptr;
     } else {
         p.C = g.C; p.ldc = g.ldc; p.strideC = g.strideC; p.strideSplit = 0;
         p.alpha = g.alpha; p.beta = g.beta;
+        p.Cin = g.beta != 0.0 ? g.Cin : nullptr;
     }
-    p.epi = EPI_NONE; p.e0 = p.e1 = nullptr; p.ei0 = p.ei1 = 0;
     const long long total = p.tiles_per_batch * g.batch * ksplit;
     JUES_REQUIRE(total < (1ll << 31), "GEMM grid too large");
 
@@ -217,7 +219,7 @@ void dgemm(jues_ctx* ctx, const GemmCall& g) {
     ctx->stats.gemm_flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)g.batch;
     ctx->stats.gemm_launches += 1;
     if (ksplit > 1)
-        splitk_reduce(ctx, work.p, ksplit, g.M, g.N, g.batch, g.alpha, g.beta, g.C, g.ldc, g.strideC);
+        splitk_reduce(ctx, work.p, ksplit, g.M, g.N, g.batch, g.alpha, g.beta, g.C, g.ldc, g.strideC, g.Cin);
 }
 
 }  // namespace jues

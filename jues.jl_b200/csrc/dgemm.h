@@ -15,6 +15,8 @@ struct GemmCall {
     double* C = nullptr;       int64_t ldc = 0; int64_t strideC = 0;
     int64_t batch = 1;
     double alpha = 1.0, beta = 0.0;
+    // beta multiplies Cin instead of C when given (same ldc / strideC as C): C = alpha*op(A)op(B) + beta*Cin
+    const double* Cin = nullptr;
     int force_cfg = -1;  // testing: pick a tile configuration explicitly
 };
 

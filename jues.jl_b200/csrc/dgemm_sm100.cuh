@@ -43,15 +43,9 @@ struct Params {
     long long ldc;
     long long strideC;
     double alpha, beta;
-    // optional fused epilogue (see Epi enum)
-    int epi;
-    const double* e0;  // epilogue operand 0
-    const double* e1;  // epilogue operand 1
-    int ei0, ei1;      // epilogue ints
-};
-
-enum Epi : int {
-    EPI_NONE = 0,  // C = alpha*acc + beta*C
+    // C = alpha*acc + beta*Cin: Cin has the layout of C (ldc, strideC); nullptr = C itself.  Lets a product
+    // start from a static tensor without a copy pass (WJ = <mj|eb> + ..., WE = -<mb|je> + ... in the CC sweep).
+    const double* Cin;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -290,7 +284,9 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
 
         // ================================= epilogue of this tile ================================
-        double* __restrict__ Cb = p.C + (long long)bz * p.strideC + (long long)zs * p.strideSplit;
+        const long long c_off = (long long)bz * p.strideC + (long long)zs * p.strideSplit;
+        double* __restrict__ Cb = p.C + c_off;
+        const double* Sb = (p.Cin ? p.Cin : p.C) + c_off;      // where the old values come from
         // Accumulating epilogue: a column's TI old values are requested back to back, and (where the
         // accumulators leave room under the 168-register limit of a 9-warp CTA) the old values of column q+1
         // BEFORE column q is stored.  Written as load, store, load, ... every load waits for a full memory
@@ -299,23 +295,24 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         constexpr bool PIPE = TI * TJ * 2 + 2 * TI <= 56;
         if (PIPE && beta != 0.0) {
             double old[TI], nxt[TI];
-            auto column = [&](int q) -> double* {
+            auto column = [&](int q) -> long long {      // element offset of column q, -1 beyond N
                 const int n = n0 + wn * WN + (q >> 1) * 8 + frag_row<B_KC>(2 * t + (q & 1));
-                return n < p.N ? Cb + (long long)n * p.ldc : nullptr;
+                return n < p.N ? (long long)n * p.ldc : -1;
             };
-            auto fetch = [&](double* col, double* dst) {
+            auto fetch = [&](long long off, double* dst) {
 #pragma unroll
                 for (int i = 0; i < TI; ++i) {
                     const int m = m0 + wm * WM + i * 8 + ra;
-                    dst[i] = (col != nullptr && m < p.M) ? __ldcg(col + m) : 0.0;
+                    dst[i] = (off >= 0 && m < p.M) ? __ldcg(Sb + off + m) : 0.0;
                 }
             };
             fetch(column(0), old);
 #pragma unroll
             for (int q = 0; q < 2 * TJ; ++q) {
-                double* col = column(q);
+                const long long off = column(q);
                 if (q + 1 < 2 * TJ) fetch(column(q + 1), nxt);
-                if (col != nullptr) {
+                if (off >= 0) {
+                    double* col = Cb + off;
 #pragma unroll
                     for (int i = 0; i < TI; ++i) {
                         const int m = m0 + wm * WM + i * 8 + ra;
@@ -333,6 +330,7 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int n = n0 + wn * WN + j * 8 + frag_row<B_KC>(2 * t + c);
                     if (n < p.N) {
                         double* col = Cb + (long long)n * p.ldc;
+                        const double* src = Sb + (long long)n * p.ldc;
                         if (beta != 0.0) {
                             // the large accumulator tiles have no registers to spare: half / a quarter of a column at a time
                             constexpr int CH = (TI * TJ >= 32) ? (TI + 3) / 4 : (TI * TJ >= 28) ? (TI + 1) / 2 : TI;
@@ -342,7 +340,7 @@ dgemm_tma_dmma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                                 for (int i = 0; i < CH; ++i) {
                                     const int m = m0 + wm * WM + (i0 + i) * 8 + ra;
-                                    old[i] = (i0 + i < TI && m < p.M) ? __ldcg(col + m) : 0.0;
+                                    old[i] = (i0 + i < TI && m < p.M) ? __ldcg(src + m) : 0.0;
                                 }
 #pragma unroll
                                 for (int i = 0; i < CH; ++i) {

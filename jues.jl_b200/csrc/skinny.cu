@@ -232,7 +232,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 bool skinny_gemm(jues_ctx* ctx, const GemmCall& g) {
     static const bool off = getenv("JUES_B200_NO_SKINNY") != nullptr;
-    if (off || g.batch != 1 || g.force_cfg >= 0) return false;
+    if (off || g.batch != 1 || g.force_cfg >= 0 || g.Cin != nullptr) return false;
     const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
     // ---- matrix-vector: N == 1, A stored K x M (k-contiguous rows) ------------------------------------------
     if (g.N == 1 && g.transA && g.M >= 256 && g.K >= 64 && g.K <= 8192) {
@@ -273,7 +273,9 @@ bool skinny_gemm(jues_ctx* ctx, const GemmCall& g) {
     // ---- K huge, M and N small ('N','T', dense operands) -----------------------------------------------------
     const double M = (double)g.M, N = (double)g.N, K = (double)g.K;
     const double intensity = 2.0 * M * N * K / (8.0 * (M * K + K * N + M * N));
-    if (!g.transA && g.transB && g.M <= 128 && g.N <= 128 && g.M * g.N <= 4096 && g.K >= 8192 && intensity < 13.0 &&
+    // (above ~1000 output elements the tile kernel with its narrow 32x128 tile and a 128-way split is faster:
+    // 20 x 100 x 200000 in 79 us against 98 us, profiles/r02/session_r02n_epilogue_narrow_tiles.log)
+    if (!g.transA && g.transB && g.M <= 128 && g.N <= 128 && g.M * g.N <= 1024 && g.K >= 8192 && intensity < 13.0 &&
         g.lda == g.M && g.ldb == g.N && (g.M & 1) == 0 && (g.N & 1) == 0 && aligned16(g.A) && aligned16(g.B)) {
         int ctas = (int)std::min<int64_t>(2 * sms, (g.K + 4 * kKC - 1) / (4 * kKC));
         KHugeArgs a;

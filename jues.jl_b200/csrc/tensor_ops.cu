@@ -136,8 +136,8 @@ __global__ void permute_tiled(const double* __restrict__ in, double* __restrict_
 
 
 __global__ void splitk_reduce_kernel(const double* __restrict__ W, int nsplit, long long M, long long N,
-                                     long long batch, double alpha, double beta, double* __restrict__ C,
-                                     long long ldc, long long strideC) {
+                                     long long batch, double alpha, double beta, double* C,
+                                     long long ldc, long long strideC, const double* Cin) {
     const long long mn = M * N;
     const long long total = mn * batch;
     long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,8 +149,8 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ W, int nsplit, l
         const double* w = W + b * (long long)nsplit * mn + e;
         double s = 0.0;
         for (int z = 0; z < nsplit; ++z) s += w[(long long)z * mn];
-        double* c = C + b * strideC + n * ldc + m;
-        *c = (beta == 0.0) ? alpha * s : alpha * s + beta * *c;
+        const long long at = b * strideC + n * ldc + m;
+        C[at] = (beta == 0.0) ? alpha * s : alpha * s + beta * Cin[at];
     }
 }
 
@@ -173,26 +173,43 @@ __global__ void tau_kernel(const double* __restrict__ T, const double* __restric
     }
 }
 
+// The "one o x o block per (a,b)" kernels below work either with one block per (a,b) pair (two block-wide
+// barriers per pair) or, when eight o x (o+1) tiles fit in shared memory (small nocc), with one WARP per pair:
+// no block-wide barrier, eight independent load streams per block.
+struct PairLoop {
+    int nw, wid, tid, nt;
+    __device__ PairLoop(bool warp_mode)
+        : nw(warp_mode ? (int)(blockDim.x >> 5) : 1), wid(warp_mode ? (int)(threadIdx.x >> 5) : 0),
+          tid(warp_mode ? (int)(threadIdx.x & 31) : (int)threadIdx.x), nt(warp_mode ? 32 : (int)blockDim.x) {}
+};
+template <bool WARP>
+__device__ __forceinline__ void pair_sync() {
+    if (WARP) __syncwarp(); else __syncthreads();
+}
+
 // All amplitude-derived operands of a sweep in ONE pass over T2 (one block per (a,b): the o x o block holds
 // both T[i,j] and T[j,i]):  Tt = 2T - T(ji),  tau = T + t(x)t,  tauh = T + 1/2 t(x)t,  Tp2 = T + 2 t(x)t.
 // Reads 8 B, writes 8 B per output element; the five separate kernels it replaces moved 2.5x as much.
+template <bool WARP>
 __global__ void amp_combos_kernel(const double* __restrict__ T, const double* __restrict__ t1,
                                   double* __restrict__ Tt, double* __restrict__ tau, double* __restrict__ tauh,
                                   double* __restrict__ Tp2, int o, int v) {
-    extern __shared__ double sh[];  // o x (o+1): sh[j*(o+1)+i] = T[i,j,a,b]
+    extern __shared__ double sh_all[];  // per pair o x (o+1): sh[j*(o+1)+i] = T[i,j,a,b]
+    const PairLoop L(WARP);
+    double* sh = sh_all + (size_t)L.wid * o * (o + 1);
     const long long oo = (long long)o * o;
     const int half = o >> 1;        // o is even: 16-byte accesses along i
-    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
+    for (long long ab = (long long)blockIdx.x * L.nw + L.wid; ab < (long long)v * v; ab += (long long)gridDim.x * L.nw) {
         const int a = (int)(ab % v), b = (int)(ab / v);
         const long long base = ab * oo;
-        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+        for (int e = L.tid; e < half * o; e += L.nt) {
             const int i = 2 * (e % half), j = e / half;
             const double2 x = *reinterpret_cast<const double2*>(T + base + i + (long long)o * j);
             sh[j * (o + 1) + i] = x.x;
             sh[j * (o + 1) + i + 1] = x.y;
         }
-        __syncthreads();
-        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+        pair_sync<WARP>();
+        for (int e = L.tid; e < half * o; e += L.nt) {
             const int i = 2 * (e % half), j = e / half;
             const long long at = base + i + (long long)o * j;
             const double x0 = sh[j * (o + 1) + i], x1 = sh[j * (o + 1) + i + 1];
@@ -207,7 +224,7 @@ __global__ void amp_combos_kernel(const double* __restrict__ T, const double* __
                 *reinterpret_cast<double2*>(Tp2 + at) = make_double2(x0 + 2.0 * tt0, x1 + 2.0 * tt1);
             }
         }
-        __syncthreads();
+        pair_sync<WARP>();
     }
 }
 
@@ -231,28 +248,31 @@ __global__ void divide_Dijab_kernel(const double* __restrict__ R, double* __rest
 // *_S arrays are (o,o,v,vs) slabs; Hfull is the complete (o,o,v,v) half residual (all-gathered).
 // One block per (a,b) pair; the o x o block H[.,.,b,a] is transposed through shared memory so that
 // every global access is coalesced.
+template <bool WARP>
 __global__ void residual_finish_kernel(const double* __restrict__ V, const double* __restrict__ L1,
                                        const double* __restrict__ L2, const double* __restrict__ H,
                                        const double* __restrict__ Hfull, double* __restrict__ Tn,
                                        const double* __restrict__ eo, const double* __restrict__ ev, int o,
                                        int v, int b0, int vs) {
-    extern __shared__ double sh[];  // o x (o+1): sh[y*(o+1)+x] = H[x,y,b,a]
+    extern __shared__ double sh_all[];  // per pair o x (o+1): sh[y*(o+1)+x] = H[x,y,b,a]
+    const PairLoop L(WARP);
+    double* sh = sh_all + (size_t)L.wid * o * (o + 1);
     const long long oo = (long long)o * o;
     const int half = o >> 1;        // o is even: 16-byte accesses along i
-    for (long long ab = blockIdx.x; ab < (long long)v * vs; ab += gridDim.x) {
+    for (long long ab = (long long)blockIdx.x * L.nw + L.wid; ab < (long long)v * vs; ab += (long long)gridDim.x * L.nw) {
         const int a = (int)(ab % v), bl = (int)(ab / v);
         const int b = b0 + bl;
         const long long base = ab * oo;                        // slab-local (a, bl)
         const long long baseT = ((long long)b + (long long)v * a) * oo;  // full (b, a)
-        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+        for (int e = L.tid; e < half * o; e += L.nt) {
             const int x = 2 * (e % half), y = e / half;
             const double2 h = *reinterpret_cast<const double2*>(Hfull + baseT + x + (long long)o * y);
             sh[y * (o + 1) + x] = h.x;
             sh[y * (o + 1) + x + 1] = h.y;
         }
-        __syncthreads();
+        pair_sync<WARP>();
         const double dab = -ev[a] - ev[b];
-        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+        for (int e = L.tid; e < half * o; e += L.nt) {
             const int i = 2 * (e % half), j = e / half;
             const long long at = base + i + (long long)o * j;
             const double2 vv = *reinterpret_cast<const double2*>(V + at);
@@ -263,7 +283,7 @@ __global__ void residual_finish_kernel(const double* __restrict__ V, const doubl
             if (L2) { const double2 l = *reinterpret_cast<const double2*>(L2 + at); r0 += l.x; r1 += l.y; }
             *reinterpret_cast<double2*>(Tn + at) = make_double2(r0 / (eo[i] + eo[j] + dab), r1 / (eo[i + 1] + eo[j] + dab));
         }
-        __syncthreads();
+        pair_sync<WARP>();
     }
 }
 
@@ -271,21 +291,26 @@ __global__ void residual_finish_kernel(const double* __restrict__ V, const doubl
 // sweep leave the GEMM in their natural layouts ([ia|jb] and [ja|ib]); one pass adds both to the half residual
 // instead of one permute-accumulate pass over H per product.  One block per (a,b): the o x o block of R2 is
 // transposed through shared memory, R1 and H move as 16-byte vectors along i (o is even).
+template <bool WARP>
 __global__ void ring_combine_kernel(const double* __restrict__ R1, const double* __restrict__ R2,
                                     double* __restrict__ H, int o, int v, int vs) {
-    extern __shared__ double sh[];  // o x (o+1): sh[i*(o+1)+j] = R2[j,a,i,b]
+    extern __shared__ double sh_all[];  // per pair o x (o+1): sh[i*(o+1)+j] = R2[j,a,i,b]
+    const PairLoop L(WARP);
+    double* sh = sh_all + (size_t)L.wid * o * (o + 1);
     const long long oo = (long long)o * o, ov = (long long)o * v;
     const int half = o >> 1;
-    for (long long ab = blockIdx.x; ab < (long long)v * vs; ab += gridDim.x) {
+    for (long long ab = (long long)blockIdx.x * L.nw + L.wid; ab < (long long)v * vs; ab += (long long)gridDim.x * L.nw) {
         const int a = (int)(ab % v), b = (int)(ab / v);
         const long long rbase = (long long)o * a + ov * o * b;     // [., a, ., b] of an (o,v,o,vs) array
-        for (int e = threadIdx.x; e < oo; e += blockDim.x) {
-            const int x = e % o, y = e / o;                        // x runs along the contiguous index j of R2
-            sh[y * (o + 1) + x] = R2[rbase + x + ov * y];
+        for (int e = L.tid; e < half * o; e += L.nt) {
+            const int x = 2 * (e % half), y = e / half;            // x runs along the contiguous index j of R2
+            const double2 r = *reinterpret_cast<const double2*>(R2 + rbase + x + ov * y);
+            sh[y * (o + 1) + x] = r.x;
+            sh[y * (o + 1) + x + 1] = r.y;
         }
-        __syncthreads();
+        pair_sync<WARP>();
         const long long hbase = ab * oo;
-        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+        for (int e = L.tid; e < half * o; e += L.nt) {
             const int i = 2 * (e % half), j = e / half;
             const double2 r1 = *reinterpret_cast<const double2*>(R1 + rbase + i + ov * j);
             double2 h = *reinterpret_cast<double2*>(H + hbase + i + (long long)o * j);
@@ -293,7 +318,7 @@ __global__ void ring_combine_kernel(const double* __restrict__ R1, const double*
             h.y += r1.y + sh[(i + 1) * (o + 1) + j];
             *reinterpret_cast<double2*>(H + hbase + i + (long long)o * j) = h;
         }
-        __syncthreads();
+        pair_sync<WARP>();
     }
 }
 
@@ -330,23 +355,26 @@ __device__ __forceinline__ double block_reduce(double v) {
 // E = sum V[ijab] (2 X[ijab] - X[jiab]), X = T + t(x)t.  One block per group of (a,b) slabs; the o x o block
 // of T goes through shared memory (its transposed partner is in the same block), V and T move as 16-byte
 // vectors along i (o is even).
+template <bool WARP>
 __global__ void cc_energy_kernel(const double* __restrict__ V, const double* __restrict__ T,
                                  const double* __restrict__ t1, int o, int v, double* __restrict__ partial) {
-    extern __shared__ double sh[];  // o x (o+1): sh[j*(o+1)+i] = T[i,j,a,b]
+    extern __shared__ double sh_all[];  // per pair o x (o+1): sh[j*(o+1)+i] = T[i,j,a,b]
+    const PairLoop L(WARP);
+    double* sh = sh_all + (size_t)L.wid * o * (o + 1);
     const long long oo = (long long)o * o;
     const int half = o >> 1;
     double acc = 0.0;
-    for (long long ab = blockIdx.x; ab < (long long)v * v; ab += gridDim.x) {
+    for (long long ab = (long long)blockIdx.x * L.nw + L.wid; ab < (long long)v * v; ab += (long long)gridDim.x * L.nw) {
         const int a = (int)(ab % v), b = (int)(ab / v);
         const long long base = ab * oo;
-        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+        for (int e = L.tid; e < half * o; e += L.nt) {
             const int i = 2 * (e % half), j = e / half;
             const double2 x = *reinterpret_cast<const double2*>(T + base + i + (long long)o * j);
             sh[j * (o + 1) + i] = x.x;
             sh[j * (o + 1) + i + 1] = x.y;
         }
-        __syncthreads();
-        for (int e = threadIdx.x; e < half * o; e += blockDim.x) {
+        pair_sync<WARP>();
+        for (int e = L.tid; e < half * o; e += L.nt) {
             const int i = 2 * (e % half), j = e / half;
             const double2 vv = *reinterpret_cast<const double2*>(V + base + i + (long long)o * j);
             double x0 = sh[j * (o + 1) + i], x1 = sh[j * (o + 1) + i + 1];
@@ -361,7 +389,7 @@ __global__ void cc_energy_kernel(const double* __restrict__ V, const double* __r
             acc += vv.x * (2.0 * x0 - xt0);
             acc += vv.y * (2.0 * x1 - xt1);
         }
-        __syncthreads();
+        pair_sync<WARP>();
     }
     const double r = block_reduce<256>(acc);
     if (threadIdx.x == 0) partial[blockIdx.x] = r;
@@ -579,6 +607,40 @@ int ew_grid(jues_ctx* ctx, size_t n, int threads) {
     JUES_CUDA(cudaGetLastError());  \
     (ctx)->stats.aux_launches++
 
+// trace level 2: one event pair around the launch, named "aux <kernel> <algorithmic MB>" (in-situ durations of
+// the HBM-bound kernels for the roofline; tools/sweep_gemm_list.py)
+struct AuxTimer {
+    Timer* t = nullptr;
+    AuxTimer(jues_ctx* ctx, const char* kernel, double bytes) {
+        if (ctx->trace >= 2) {
+            char nm[64];
+            snprintf(nm, sizeof nm, "aux %s %.1fMB", kernel, bytes * 1e-6);
+            t = new Timer(ctx, nm);
+        }
+    }
+    ~AuxTimer() { delete t; }
+};
+
+// launch geometry of the "one o x o block per (a,b)" kernels: warp-per-pair when eight tiles fit in 48 KB
+struct PairLaunch { bool warp; unsigned blocks; size_t smem; };
+static PairLaunch pair_launch(jues_ctx* ctx, int64_t o, long long pairs, const char* who) {
+    const size_t tile = (size_t)o * (o + 1) * sizeof(double);
+    JUES_REQUIRE((o & 1) == 0, "padded nocc must be even");
+    if (tile > 200 * 1024) throw Error(JUES_B200_EINVAL, std::string("invalid argument: ") + who + ": nocc too large for the shared-memory block (padded nocc <= 158)");
+    PairLaunch p;
+    p.warp = 8 * tile <= 48 * 1024;
+    const long long want = p.warp ? (pairs + 7) / 8 : pairs;
+    const long long cap = (long long)ctx->sm_count * 16;
+    p.blocks = (unsigned)std::max<long long>(1, std::min(want, cap));
+    p.smem = p.warp ? 8 * tile : tile;
+    return p;
+}
+template <class K>
+static void raise_smem(jues_ctx* ctx, K kernel) {
+    if (ctx->smem_attr_done.insert((const void*)kernel).second)
+        JUES_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
+
 void fill_pattern(jues_ctx* ctx, double* p, size_t n, unsigned long long seed) {
     fill_pattern_kernel<<<ew_grid(ctx, n, 256), 256, 0, ctx->stream>>>(p, n, seed);
     AUX_LAUNCHED(ctx);
@@ -687,10 +749,11 @@ void permute_axpby_strided(jues_ctx* ctx, double alpha, const Ten& in, const int
 }
 
 void splitk_reduce(jues_ctx* ctx, const double* W, int nsplit, int64_t M, int64_t N, int64_t batch,
-                   double alpha, double beta, double* C, int64_t ldc, int64_t strideC) {
+                   double alpha, double beta, double* C, int64_t ldc, int64_t strideC, const double* Cin) {
     const size_t total = (size_t)M * N * batch;
+    AuxTimer tm(ctx, "splitk_reduce", 8.0 * (double)total * (nsplit + 1.0 + (beta != 0.0 ? 1.0 : 0.0)));
     splitk_reduce_kernel<<<ew_grid(ctx, total, 256), 256, 0, ctx->stream>>>(W, nsplit, M, N, batch, alpha,
-                                                                            beta, C, ldc, strideC);
+                                                                            beta, C, ldc, strideC, Cin ? Cin : C);
     AUX_LAUNCHED(ctx);
 }
 
@@ -702,16 +765,15 @@ void tau_build(jues_ctx* ctx, const double* T, const double* t1, double c, doubl
 
 void amp_combos(jues_ctx* ctx, const double* T, const double* t1, double* Tt, double* tau, double* tauh,
                 double* Tp2, int64_t o, int64_t v) {
-    const size_t smem = (size_t)o * (o + 1) * sizeof(double);
-    JUES_REQUIRE(smem <= 200 * 1024, "amp_combos: nocc too large for the shared-memory block");
-    JUES_REQUIRE((o & 1) == 0, "amp_combos: padded nocc must be even");
-    if (ctx->smem_attr_done.insert((const void*)amp_combos_kernel).second)
-        JUES_CUDA(cudaFuncSetAttribute(amp_combos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    long long blocks = (long long)v * v;
-    const long long cap = (long long)ctx->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) return;
-    amp_combos_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(T, t1, Tt, tau, tauh, Tp2, (int)o, (int)v);
+    if (v == 0) return;
+    const PairLaunch g = pair_launch(ctx, o, (long long)v * v, "amp_combos");
+    AuxTimer tm(ctx, "amp_combos", 8.0 * (double)(o * o * v * v) * (t1 ? 5.0 : 2.0));
+    if (g.warp) {
+        amp_combos_kernel<true><<<g.blocks, 256, g.smem, ctx->stream>>>(T, t1, Tt, tau, tauh, Tp2, (int)o, (int)v);
+    } else {
+        raise_smem(ctx, amp_combos_kernel<false>);
+        amp_combos_kernel<false><<<g.blocks, 256, g.smem, ctx->stream>>>(T, t1, Tt, tau, tauh, Tp2, (int)o, (int)v);
+    }
     AUX_LAUNCHED(ctx);
 }
 
@@ -725,32 +787,30 @@ void divide_Dijab(jues_ctx* ctx, const double* R, double* Tnew, const double* eo
 void residual_finish(jues_ctx* ctx, const double* V, const double* L1, const double* L2, const double* H,
                      const double* Hfull, double* Tnew, const double* eo, const double* ev, int64_t o,
                      int64_t v, int64_t b0, int64_t vs) {
-    const size_t smem = (size_t)o * (o + 1) * sizeof(double);
-    JUES_REQUIRE(smem <= 200 * 1024, "residual_finish: nocc too large for the shared-memory slab");
-    JUES_REQUIRE((o & 1) == 0, "residual_finish: padded nocc must be even");
-    if (ctx->smem_attr_done.insert((const void*)residual_finish_kernel).second)
-        JUES_CUDA(cudaFuncSetAttribute(residual_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024));
-    long long blocks = (long long)v * vs;
-    if (blocks == 0) return;
-    const long long cap = (long long)ctx->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    residual_finish_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(V, L1, L2, H, Hfull, Tnew, eo, ev,
-                                                                         (int)o, (int)v, (int)b0, (int)vs);
+    if (v * vs == 0) return;
+    const PairLaunch g = pair_launch(ctx, o, (long long)v * vs, "residual_finish");
+    AuxTimer tm(ctx, "residual_finish", 8.0 * (double)(o * o * v * vs) * (4.0 + (L1 ? 1.0 : 0.0) + (L2 ? 1.0 : 0.0)));
+    if (g.warp) {
+        residual_finish_kernel<true><<<g.blocks, 256, g.smem, ctx->stream>>>(V, L1, L2, H, Hfull, Tnew, eo, ev, (int)o,
+                                                                             (int)v, (int)b0, (int)vs);
+    } else {
+        raise_smem(ctx, residual_finish_kernel<false>);
+        residual_finish_kernel<false><<<g.blocks, 256, g.smem, ctx->stream>>>(V, L1, L2, H, Hfull, Tnew, eo, ev, (int)o,
+                                                                              (int)v, (int)b0, (int)vs);
+    }
     AUX_LAUNCHED(ctx);
 }
 
 void ring_combine(jues_ctx* ctx, const double* R1, const double* R2, double* H, int64_t o, int64_t v, int64_t vs) {
-    const size_t smem = (size_t)o * (o + 1) * sizeof(double);
-    JUES_REQUIRE((o & 1) == 0, "ring_combine: padded nocc must be even");
-    JUES_REQUIRE(smem <= 200 * 1024, "ring_combine: nocc too large for the shared-memory block");
-    if (ctx->smem_attr_done.insert((const void*)ring_combine_kernel).second)
-        JUES_CUDA(cudaFuncSetAttribute(ring_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    long long blocks = (long long)v * vs;
-    if (blocks == 0) return;
-    const long long cap = (long long)ctx->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    ring_combine_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(R1, R2, H, (int)o, (int)v, (int)vs);
+    if (v * vs == 0) return;
+    const PairLaunch g = pair_launch(ctx, o, (long long)v * vs, "ring_combine");
+    AuxTimer tm(ctx, "ring_combine", 8.0 * (double)(o * o * v * vs) * 4.0);
+    if (g.warp) {
+        ring_combine_kernel<true><<<g.blocks, 256, g.smem, ctx->stream>>>(R1, R2, H, (int)o, (int)v, (int)vs);
+    } else {
+        raise_smem(ctx, ring_combine_kernel<false>);
+        ring_combine_kernel<false><<<g.blocks, 256, g.smem, ctx->stream>>>(R1, R2, H, (int)o, (int)v, (int)vs);
+    }
     AUX_LAUNCHED(ctx);
 }
 
@@ -769,36 +829,29 @@ static double finish_reduction(jues_ctx* ctx, int nblocks) {
     return ctx->red_host[0];
 }
 
-static int reduction_blocks(jues_ctx* ctx, int64_t v) {
-    long long blocks = (long long)v * v;
-    const long long cap = (long long)ctx->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks > (long long)ctx->red_cap - 2) blocks = (long long)ctx->red_cap - 2;
-    return (int)blocks;
-}
-
-static size_t cc_energy_smem(jues_ctx* ctx, int64_t o) {
-    const size_t smem = (size_t)o * (o + 1) * sizeof(double);
-    JUES_REQUIRE(smem <= 200 * 1024, "cc_energy: nocc too large for the shared-memory block");
-    JUES_REQUIRE((o & 1) == 0, "cc_energy: padded nocc must be even");
-    if (ctx->smem_attr_done.insert((const void*)cc_energy_kernel).second)
-        JUES_CUDA(cudaFuncSetAttribute(cc_energy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    return smem;
+static int cc_energy_launch(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v) {
+    PairLaunch g = pair_launch(ctx, o, (long long)v * v, "cc_energy");
+    AuxTimer tm(ctx, "cc_energy", 8.0 * (double)(o * o * v * v) * 2.0);
+    g.blocks = (unsigned)std::min<long long>(g.blocks, (long long)ctx->red_cap - 2);
+    if (g.warp) {
+        cc_energy_kernel<true><<<g.blocks, 256, g.smem, ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
+    } else {
+        raise_smem(ctx, cc_energy_kernel<false>);
+        cc_energy_kernel<false><<<g.blocks, 256, g.smem, ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
+    }
+    AUX_LAUNCHED(ctx);
+    return (int)g.blocks;
 }
 
 void cc_energy_async(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v,
                      double* dev_out) {
-    const int blocks = reduction_blocks(ctx, v);
-    cc_energy_kernel<<<blocks, 256, cc_energy_smem(ctx, o), ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
-    AUX_LAUNCHED(ctx);
+    const int blocks = cc_energy_launch(ctx, V, T, t1, o, v);
     final_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, blocks, dev_out);
     AUX_LAUNCHED(ctx);
 }
 
 double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v) {
-    const int blocks = reduction_blocks(ctx, v);
-    cc_energy_kernel<<<blocks, 256, cc_energy_smem(ctx, o), ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
-    AUX_LAUNCHED(ctx);
+    const int blocks = cc_energy_launch(ctx, V, T, t1, o, v);
     return finish_reduction(ctx, blocks);
 }
 
@@ -839,12 +892,14 @@ void pack_vvvv_sa(jues_ctx* ctx, const double* W4, int64_t v, int64_t b0, int64_
 void pack_tau_sa(jues_ctx* ctx, const double* tau, int64_t oo, int64_t v, int64_t ldk, double* Tpm) {
     const int64_t np = sa_pairs(v);
     const int threads = oo >= 256 ? 256 : (oo >= 128 ? 128 : 64);
+    AuxTimer tm(ctx, "pack_tau_sa", 8.0 * (double)(oo * v * v) * 2.0);
     long long blocks = std::min<long long>(np, (long long)ctx->sm_count * 16);
     pack_tau_sa_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(tau, (int)oo, (int)v, np, Tpm, Tpm + oo * ldk);
     AUX_LAUNCHED(ctx);
 }
 
 void unpack_ladder_sa(jues_ctx* ctx, const double* Lpm, int64_t oo, int64_t v, int64_t b0, int64_t vs, double* out) {
+    AuxTimer tm(ctx, "unpack_ladder_sa", 8.0 * (double)(oo * v * vs) * 2.0);
     const int threads = oo >= 256 ? 256 : (oo >= 128 ? 128 : 64);
     long long blocks = std::min<long long>(v * vs, (long long)ctx->sm_count * 16);
     if (blocks < 1) return;

@@ -58,9 +58,11 @@ void axpby(jues_ctx* ctx, size_t n, double a, const double* x, double b, double*
 void lincomb2(jues_ctx* ctx, size_t n, double a, const double* x1, double b, const double* x2, double* y);
 void fill(jues_ctx* ctx, double* p, size_t n, double v);
 
-// split-K epilogue: C[m,n] = alpha * sum_z W[z][m,n] + beta * C[m,n]   (W slices dense M x N)
+// split-K epilogue: C[m,n] = alpha * sum_z W[z][m,n] + beta * Cin[m,n]   (W slices dense M x N; Cin has
+// the layout of C, nullptr = C itself)
 void splitk_reduce(jues_ctx* ctx, const double* W, int nsplit, int64_t M, int64_t N, int64_t batch,
-                   double alpha, double beta, double* C, int64_t ldc, int64_t strideC);
+                   double alpha, double beta, double* C, int64_t ldc, int64_t strideC,
+                   const double* Cin = nullptr);
 
 // out[i,j,a,b] = T[i,j,a,b] + c * t[i,a] * t[j,b]        (o,o,v,v), t is (o,v); T may be null (=0)
 void tau_build(jues_ctx* ctx, const double* T, const double* t1, double c, double* out, int64_t o, int64_t v);
