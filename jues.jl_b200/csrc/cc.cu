@@ -156,6 +156,10 @@ struct CC {
     // DF-RCCD.jl:256 contracts <mn|ef> where RCCD.jl:402 contracts <nm|ef> in the third term of WmBeJ, i.e. its
     // ring intermediate is <mb|ej> + 1/2 <mn|ef> (T[njfb] - T[jnfb]): the density-fitted driver follows its file
     bool df_wmbej = false;
+    static bool no_amp_extras() {
+        static const bool off = getenv("JUES_B200_NO_AMP_EXTRAS") != nullptr;     // A/B switch for measurements
+        return off;
+    }
     // off-diagonal Fock blocks of a non-canonical reference (AutoRCCSD.jl:218-231), zero diagonals,
     // zero padding:  foT[m,i] = f[i,m] (o,o),  fov[m,e] (o,v),  fvv[e,a] (v,v).  fock == false: canonical.
     DTen foT, fov, fvv;
@@ -331,16 +335,36 @@ struct CC {
         DTen tau, tauh, Tt, Tp2;
         Tt.alloc(ctx, o, o, v, v);
         Ten tauv = T, tauhv = T;
+        // ... and, in the same pass, the operand layouts the ring / Fae products of this sweep want (each one
+        // a permutation pass less): handed to contract() through the PermCache under the keys it will look up
+        AmpExtras ex;
+        DBuf xb[6];
+        if (relaid && !no_amp_extras()) {
+            const size_t nfull = (size_t)(o * o * v * v), nslab = (size_t)(o * o * v * vs);
+            for (int q = 0; q < 6; ++q) xb[q].alloc(ctx, q < 3 ? nfull : nslab);
+            ex.T_meia = xb[0].p; ex.Tt_meia = xb[1].p; ex.T_meja = xb[2].p;
+            ex.T_nfjb = xb[3].p; ex.X_nfjb = xb[4].p; ex.Y_mnfa = xb[5].p;
+            ex.b0 = (int)b0; ex.vs = (int)vs;
+        }
         if (singles) {
             tau.alloc(ctx, o, o, v, v); tauh.alloc(ctx, o, o, v, v); Tp2.alloc(ctx, o, o, v, v);
-            amp_combos(ctx, T.p, t.p, Tt.p(), tau.p(), tauh.p(), Tp2.p(), o, v);
+            amp_combos(ctx, T.p, t.p, Tt.p(), tau.p(), tauh.p(), Tp2.p(), o, v, &ex);
             tauv = tau; tauhv = tauh;
         } else {
-            amp_combos(ctx, T.p, nullptr, Tt.p(), nullptr, nullptr, nullptr, o, v);
+            amp_combos(ctx, T.p, nullptr, Tt.p(), nullptr, nullptr, nullptr, o, v, &ex);
         }
         const Ten tau_S = last_slab(tauv, b0, vs), tauh_S = last_slab(tauhv, b0, vs);
         pcache.add(T, true); pcache.add(Tt, true);
         if (singles) { pcache.add(tau, true); pcache.add(tauh, true); }
+        if (ex.T_meia) {
+            // the index strings are those of the contract() calls below
+            pcache.provide(perm_key(T, "imae", "meia"), std::move(xb[0]));
+            pcache.provide(perm_key(Tt, "imae", "meia"), std::move(xb[1]));
+            pcache.provide(perm_key(T, "mjae", "meja"), std::move(xb[2]));
+            pcache.provide(perm_key(T_S, "njfb", "nfjb"), std::move(xb[3]));
+            pcache.provide(perm_key(singles ? last_slab(Tp2, b0, vs) : T_S, "jnfb", "nfjb"), std::move(xb[4]));
+            pcache.provide(perm_key(tauh_S, "mnaf", "mnfa"), std::move(xb[5]));
+        }
 
         // ---- small intermediates: partial sums over f in the slab, one all-reduce -------------------
         TraceTimer* tr_small = new TraceTimer(ctx, "cc.part.small");

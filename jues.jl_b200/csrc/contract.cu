@@ -39,11 +39,9 @@ const double* permuted_operand(jues_ctx* ctx, const Ten& X, const char* ix, cons
     if (pc) {
         for (const auto& r : pc->ranges) {
             if (X.p < r.lo || X.p >= r.hi) continue;
-            char key[160];
-            snprintf(key, sizeof key, "%p:%lld,%lld,%lld,%lld:%s>%s", (const void*)X.p, (long long)X.d[0],
-                     (long long)X.d[1], (long long)X.d[2], (long long)X.d[3], ix, tgt.c_str());
+            const std::string key = perm_key(X, ix, tgt);
             for (auto& e : pc->entries)
-                if (e.key == key) return e.buf.p;
+                if (e.key == key) { ++e.hits; return e.buf.p; }
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);
             const size_t bytes = (size_t)X.size() * 8;
@@ -73,6 +71,13 @@ const double* permuted_operand(jues_ctx* ctx, const Ten& X, const char* ix, cons
 }
 
 }  // namespace
+
+std::string perm_key(const Ten& X, const char* ix, const std::string& tgt) {
+    char key[160];
+    snprintf(key, sizeof key, "%p:%lld,%lld,%lld,%lld:%s>%s", (const void*)X.p, (long long)X.d[0],
+             (long long)X.d[1], (long long)X.d[2], (long long)X.d[3], ix, tgt.c_str());
+    return key;
+}
 
 void contract(jues_ctx* ctx, double alpha, const Ten& A, const char* ia, const Ten& B, const char* ib,
               double beta, const Ten& C, const char* ic, bool batch_last, const double* Cin) {

@@ -12,10 +12,17 @@ namespace jues {
 // static integrals are permuted once per calculation, amplitude-derived tensors once per sweep.
 struct PermCache {
     struct Range { const double* lo; const double* hi; bool sweep; };
-    struct Entry { std::string key; DBuf buf; bool sweep; };
+    struct Entry { std::string key; DBuf buf; bool sweep; long long hits = 0; };
     std::vector<Range> ranges;
     std::vector<Entry> entries;
     void add(const Ten& t, bool sweep) { ranges.push_back({t.p, t.p + t.size(), sweep}); }
+    // a permuted copy somebody else already made (amp_combos writes the operand layouts of the sweep's ring
+    // and Fae products while it has the amplitudes in shared memory): contract() finds it under `key`
+    void provide(const std::string& key, DBuf&& buf) {
+        Entry e;
+        e.key = key; e.buf = std::move(buf); e.sweep = true;
+        entries.push_back(std::move(e));
+    }
     // drop everything derived from per-sweep tensors
     void end_sweep() {
         for (size_t k = 0; k < entries.size();)
@@ -25,6 +32,9 @@ struct PermCache {
     }
     void clear() { entries.clear(); ranges.clear(); }
 };
+
+// key of the permuted copy of X (axes ix) in axis order tgt
+std::string perm_key(const Ten& X, const char* ix, const std::string& tgt);
 
 // C[ic] = alpha * sum_{shared letters} A[ia] * B[ib] + beta * C[ic]
 // batch_last: the last letter of ic (also the last letter of ia and/or ib) is a batch index -- one batched

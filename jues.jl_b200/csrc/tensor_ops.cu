@@ -193,11 +193,11 @@ __device__ __forceinline__ void pair_sync() {
 template <bool WARP>
 __global__ void amp_combos_kernel(const double* __restrict__ T, const double* __restrict__ t1,
                                   double* __restrict__ Tt, double* __restrict__ tau, double* __restrict__ tauh,
-                                  double* __restrict__ Tp2, int o, int v) {
+                                  double* __restrict__ Tp2, int o, int v, const AmpExtras ex) {
     extern __shared__ double sh_all[];  // per pair o x (o+1): sh[j*(o+1)+i] = T[i,j,a,b]
     const PairLoop L(WARP);
     double* sh = sh_all + (size_t)L.wid * o * (o + 1);
-    const long long oo = (long long)o * o;
+    const long long oo = (long long)o * o, ov = (long long)o * v;
     const int half = o >> 1;        // o is even: 16-byte accesses along i
     for (long long ab = (long long)blockIdx.x * L.nw + L.wid; ab < (long long)v * v; ab += (long long)gridDim.x * L.nw) {
         const int a = (int)(ab % v), b = (int)(ab / v);
@@ -209,19 +209,42 @@ __global__ void amp_combos_kernel(const double* __restrict__ T, const double* __
             sh[j * (o + 1) + i + 1] = x.y;
         }
         pair_sync<WARP>();
+        const int bl = b - ex.b0;
+        const bool in_slab = bl >= 0 && bl < ex.vs;
         for (int e = L.tid; e < half * o; e += L.nt) {
-            const int i = 2 * (e % half), j = e / half;
-            const long long at = base + i + (long long)o * j;
-            const double x0 = sh[j * (o + 1) + i], x1 = sh[j * (o + 1) + i + 1];
-            const double xt0 = sh[i * (o + 1) + j], xt1 = sh[(i + 1) * (o + 1) + j];
+            // p runs along the fastest index of every output; (p,q) is element (i=p, j=q) for the outputs in
+            // the layout of T and element (i=q, j=p) for the transposed ones
+            const int p = 2 * (e % half), q = e / half;
+            const long long at = base + p + (long long)o * q;
+            const double x0 = sh[q * (o + 1) + p], x1 = sh[q * (o + 1) + p + 1];        // T[p,q], T[p+1,q]
+            const double xt0 = sh[p * (o + 1) + q], xt1 = sh[(p + 1) * (o + 1) + q];    // T[q,p], T[q,p+1]
             *reinterpret_cast<double2*>(Tt + at) = make_double2(2.0 * x0 - xt0, 2.0 * x1 - xt1);
+            double tt0 = 0.0, tt1 = 0.0, ts0 = 0.0, ts1 = 0.0;
             if (t1) {
-                const double2 ta = *reinterpret_cast<const double2*>(t1 + i + (long long)o * a);
-                const double tb = t1[j + (long long)o * b];
-                const double tt0 = ta.x * tb, tt1 = ta.y * tb;
+                const double2 ta = *reinterpret_cast<const double2*>(t1 + p + (long long)o * a);
+                const double tb = t1[q + (long long)o * b];
+                tt0 = ta.x * tb; tt1 = ta.y * tb;                                      // t[p,a] t[q,b]
                 *reinterpret_cast<double2*>(tau + at) = make_double2(x0 + tt0, x1 + tt1);
                 *reinterpret_cast<double2*>(tauh + at) = make_double2(x0 + 0.5 * tt0, x1 + 0.5 * tt1);
                 *reinterpret_cast<double2*>(Tp2 + at) = make_double2(x0 + 2.0 * tt0, x1 + 2.0 * tt1);
+                if (ex.X_nfjb && in_slab) {
+                    const double2 tb2 = *reinterpret_cast<const double2*>(t1 + p + (long long)o * b);
+                    const double tqa = t1[q + (long long)o * a];
+                    ts0 = tqa * tb2.x; ts1 = tqa * tb2.y;                              // t[q,a] t[p,b]
+                }
+            }
+            // [., b | ., a] position of an (o,v,o,v) operand: run index + o*b + o*v*(other + o*a)
+            const long long ra = p + (long long)o * b + ov * (q + (long long)o * a);
+            if (ex.T_meia) *reinterpret_cast<double2*>(ex.T_meia + ra) = make_double2(xt0, xt1);
+            if (ex.Tt_meia) *reinterpret_cast<double2*>(ex.Tt_meia + ra) = make_double2(2.0 * xt0 - x0, 2.0 * xt1 - x1);
+            if (ex.T_meja) *reinterpret_cast<double2*>(ex.T_meja + ra) = make_double2(x0, x1);
+            if (in_slab) {
+                const long long rs = p + (long long)o * a + ov * (q + (long long)o * bl);   // [., a | ., b in S]
+                if (ex.T_nfjb) *reinterpret_cast<double2*>(ex.T_nfjb + rs) = make_double2(x0, x1);
+                if (ex.X_nfjb) *reinterpret_cast<double2*>(ex.X_nfjb + rs) = make_double2(xt0 + 2.0 * ts0, xt1 + 2.0 * ts1);
+                if (ex.Y_mnfa)
+                    *reinterpret_cast<double2*>(ex.Y_mnfa + p + (long long)o * q + oo * (bl + (long long)ex.vs * a)) =
+                        make_double2(x0 + 0.5 * tt0, x1 + 0.5 * tt1);
             }
         }
         pair_sync<WARP>();
@@ -367,27 +390,52 @@ __global__ void cc_energy_kernel(const double* __restrict__ V, const double* __r
     for (long long ab = (long long)blockIdx.x * L.nw + L.wid; ab < (long long)v * v; ab += (long long)gridDim.x * L.nw) {
         const int a = (int)(ab % v), b = (int)(ab / v);
         const long long base = ab * oo;
-        for (int e = L.tid; e < half * o; e += L.nt) {
-            const int i = 2 * (e % half), j = e / half;
-            const double2 x = *reinterpret_cast<const double2*>(T + base + i + (long long)o * j);
-            sh[j * (o + 1) + i] = x.x;
-            sh[j * (o + 1) + i + 1] = x.y;
+        // four independent 16-byte loads in flight per thread in both passes (a pure-read kernel: with one
+        // load per loop trip the FMA chain behind it serialises the memory requests)
+        const int n2 = half * o;
+        for (int e0 = L.tid; e0 < n2; e0 += 4 * L.nt) {
+            double2 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * L.nt;
+                if (e < n2) x[u] = *reinterpret_cast<const double2*>(T + base + 2 * (e % half) + (long long)o * (e / half));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * L.nt;
+                if (e < n2) {
+                    const int i = 2 * (e % half), j = e / half;
+                    sh[j * (o + 1) + i] = x[u].x;
+                    sh[j * (o + 1) + i + 1] = x[u].y;
+                }
+            }
         }
         pair_sync<WARP>();
-        for (int e = L.tid; e < half * o; e += L.nt) {
-            const int i = 2 * (e % half), j = e / half;
-            const double2 vv = *reinterpret_cast<const double2*>(V + base + i + (long long)o * j);
-            double x0 = sh[j * (o + 1) + i], x1 = sh[j * (o + 1) + i + 1];
-            double xt0 = sh[i * (o + 1) + j], xt1 = sh[(i + 1) * (o + 1) + j];
-            if (t1) {
-                const double2 tia = *reinterpret_cast<const double2*>(t1 + i + (long long)o * a);
-                const double2 tib = *reinterpret_cast<const double2*>(t1 + i + (long long)o * b);
-                const double tjb = t1[j + (long long)o * b], tja = t1[j + (long long)o * a];
-                x0 += tia.x * tjb; x1 += tia.y * tjb;
-                xt0 += tja * tib.x; xt1 += tja * tib.y;
+        for (int e0 = L.tid; e0 < n2; e0 += 4 * L.nt) {
+            double2 vq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * L.nt;
+                if (e < n2) vq[u] = *reinterpret_cast<const double2*>(V + base + 2 * (e % half) + (long long)o * (e / half));
             }
-            acc += vv.x * (2.0 * x0 - xt0);
-            acc += vv.y * (2.0 * x1 - xt1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * L.nt;
+                if (e >= n2) continue;
+                const int i = 2 * (e % half), j = e / half;
+                const double2 vv = vq[u];
+                double x0 = sh[j * (o + 1) + i], x1 = sh[j * (o + 1) + i + 1];
+                double xt0 = sh[i * (o + 1) + j], xt1 = sh[(i + 1) * (o + 1) + j];
+                if (t1) {
+                    const double2 tia = *reinterpret_cast<const double2*>(t1 + i + (long long)o * a);
+                    const double2 tib = *reinterpret_cast<const double2*>(t1 + i + (long long)o * b);
+                    const double tjb = t1[j + (long long)o * b], tja = t1[j + (long long)o * a];
+                    x0 += tia.x * tjb; x1 += tia.y * tjb;
+                    xt0 += tja * tib.x; xt1 += tja * tib.y;
+                }
+                acc += vv.x * (2.0 * x0 - xt0);
+                acc += vv.y * (2.0 * x1 - xt1);
+            }
         }
         pair_sync<WARP>();
     }
@@ -764,15 +812,19 @@ void tau_build(jues_ctx* ctx, const double* T, const double* t1, double c, doubl
 }
 
 void amp_combos(jues_ctx* ctx, const double* T, const double* t1, double* Tt, double* tau, double* tauh,
-                double* Tp2, int64_t o, int64_t v) {
+                double* Tp2, int64_t o, int64_t v, const AmpExtras* extras) {
     if (v == 0) return;
+    const AmpExtras ex = extras ? *extras : AmpExtras();
+    double outs = t1 ? 4.0 : 1.0;
+    for (const double* q : {ex.T_meia, ex.Tt_meia, ex.T_meja}) outs += q ? 1.0 : 0.0;
+    for (const double* q : {ex.T_nfjb, ex.X_nfjb, ex.Y_mnfa}) outs += q ? (double)ex.vs / (double)v : 0.0;
+    AuxTimer tm(ctx, "amp_combos", 8.0 * (double)(o * o * v * v) * (1.0 + outs));
     const PairLaunch g = pair_launch(ctx, o, (long long)v * v, "amp_combos");
-    AuxTimer tm(ctx, "amp_combos", 8.0 * (double)(o * o * v * v) * (t1 ? 5.0 : 2.0));
     if (g.warp) {
-        amp_combos_kernel<true><<<g.blocks, 256, g.smem, ctx->stream>>>(T, t1, Tt, tau, tauh, Tp2, (int)o, (int)v);
+        amp_combos_kernel<true><<<g.blocks, 256, g.smem, ctx->stream>>>(T, t1, Tt, tau, tauh, Tp2, (int)o, (int)v, ex);
     } else {
         raise_smem(ctx, amp_combos_kernel<false>);
-        amp_combos_kernel<false><<<g.blocks, 256, g.smem, ctx->stream>>>(T, t1, Tt, tau, tauh, Tp2, (int)o, (int)v);
+        amp_combos_kernel<false><<<g.blocks, 256, g.smem, ctx->stream>>>(T, t1, Tt, tau, tauh, Tp2, (int)o, (int)v, ex);
     }
     AUX_LAUNCHED(ctx);
 }
@@ -899,7 +951,7 @@ void pack_tau_sa(jues_ctx* ctx, const double* tau, int64_t oo, int64_t v, int64_
 }
 
 void unpack_ladder_sa(jues_ctx* ctx, const double* Lpm, int64_t oo, int64_t v, int64_t b0, int64_t vs, double* out) {
-    AuxTimer tm(ctx, "unpack_ladder_sa", 8.0 * (double)(oo * v * vs) * 2.0);
+    AuxTimer tm(ctx, "unpack_ladder_sa", 8.0 * (double)(oo * v * vs) * 3.0);   // every [L+|L-] element serves (a,b) and (b,a)
     const int threads = oo >= 256 ? 256 : (oo >= 128 ? 128 : 64);
     long long blocks = std::min<long long>(v * vs, (long long)ctx->sm_count * 16);
     if (blocks < 1) return;

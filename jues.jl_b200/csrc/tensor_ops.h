@@ -69,8 +69,20 @@ void tau_build(jues_ctx* ctx, const double* T, const double* t1, double c, doubl
 
 // One pass over T2 (o,o,v,v): Tt = 2T - T(ji); with t1 (o,v) also tau = T + t(x)t, tauh = T + 1/2 t(x)t,
 // Tp2 = T + 2 t(x)t  (t1 == nullptr: only Tt is written, the other outputs may be null)
+// Optional extra outputs: operand layouts of the sweep's ring / Fae products, written while the o x o block
+// is in shared memory (each replaces a separate permutation pass: 16 B read + written per element saved).
+// S = the slab [b0, b0+vs) of the last index; X = Tp2 with singles, T without; Y = tauh with singles, T without.
+struct AmpExtras {
+    double* T_meia = nullptr;    // [m,e,i,a] = T[i,m,a,e]              (o,v,o,v)
+    double* Tt_meia = nullptr;   // [m,e,i,a] = Tt[i,m,a,e]
+    double* T_meja = nullptr;    // [m,e,j,a] = T[m,j,a,e]
+    double* T_nfjb = nullptr;    // [n,f,j,b] = T[n,j,f,b], b in S      (o,v,o,vs)
+    double* X_nfjb = nullptr;    // [n,f,j,b] = X[j,n,f,b], b in S
+    double* Y_mnfa = nullptr;    // [m,n,f,a] = Y[m,n,a,f], f in S      (o,o,vs,v)
+    int b0 = 0, vs = 0;
+};
 void amp_combos(jues_ctx* ctx, const double* T, const double* t1, double* Tt, double* tau, double* tauh,
-                double* Tp2, int64_t o, int64_t v);
+                double* Tp2, int64_t o, int64_t v, const AmpExtras* extras = nullptr);
 
 // Tnew[i,j,a,b] = R[i,j,a,b] / (eo[i] + eo[j] - ev[a] - ev[b])       (may be in place)
 void divide_Dijab(jues_ctx* ctx, const double* R, double* Tnew, const double* eo, const double* ev,

@@ -308,6 +308,29 @@ function mrccd(refWfn; maxit=40, doprint=false, return_T2=false)      # mRCCD.jl
     return_T2 ? (e[], T2) : e[]                                       # mRCCD.jl:115-119
 end
 
+# density-fitted variants: pqP (nao,nao,naux), Jpqh (naux,naux) as DF.setup_df returns them (DF.jl:30-51)
+function df_rmp2(refWfn, pqP::Array{Float64,3}, Jpqh::Array{Float64,2})          # DF-RMP2.jl:1
+    e = Ref{Float64}(0.0)
+    o, v = refWfn.nalpha, refWfn.nvira
+    check(ccall(sym(:jues_b200_df_rmp2), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
+                 Ptr{Float64}, Ref{Float64}),
+                ctx[], pqP, size(pqP, 1), size(pqP, 3), Jpqh, refWfn.Cao, o, refWfn.Cav, v, refWfn.epsa, e))
+    e[]
+end
+
+function df_rccd(refWfn, pqP::Array{Float64,3}, Jpqh::Array{Float64,2}; maxit=40, return_T2=false)   # DF-RCCD.jl:11
+    e = Ref{Float64}(0.0)
+    o, v = refWfn.nalpha, refWfn.nvira
+    T2 = return_T2 ? Array{Float64}(undef, o, o, v, v) : C_NULL
+    check(ccall(sym(:jues_b200_df_rccd), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
+                 Ptr{Float64}, Cint, Ref{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx[], pqP, size(pqP, 1), size(pqP, 3), Jpqh, refWfn.Cao, o, refWfn.Cav, v, refWfn.epsa, maxit, e,
+                C_NULL, T2))
+    return_T2 ? (e[], T2) : e[]                                                  # DF-RCCD.jl:47-52
+end
+
 function compute_pT(; T1::Array{Float64,2}, T2::Array{Float64,4}, Vvvvo::Array{Float64,4},
                     Vvooo::Array{Float64,4}, Vvovo::Array{Float64,4}, fo::Array{Float64,1}, fv::Array{Float64,1})
     o, v = size(T1)                                                   # PerturbativeTriples.jl:39
