@@ -646,17 +646,6 @@ def gpu_arm(args, rank, world):
                   "golden": gold_path,
                   "oracle": (str(gold["model"]) if "model" in gold.files else
                              "oracle/jues_oracle.py (literal RCCSD.jl:150-289)") + ", tests/golden/make_bench_golden.py"}
-    # ---- CPU baseline on this box's host cores (rank 0, N=1 only), bounded sample ------------
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        t_tr, t_it, e_cpu, how = run_oracle_sample(nbf, NOCC, 1, True)
-        info = cpu_info()
-        cpu = {"value": fl.rccsd_iter_ref(o, v) / t_it * 1e-12, "unit": "TFLOP/s",
-               "cores": info["blas_threads"] or info["host_cores"],
-               "kind": "port", "s_per_iteration": t_it, "s_transforms": t_tr,
-               "sample": f"oracle (numpy/OpenBLAS port of the reference's literal algorithm): 15 transforms "
-                         f"({t_tr:.1f} s) + 1 sweep ({t_it:.1f} s) at nbf={nbf} nocc={NOCC}; value = F_ref / s",
-               "energy_check": abs(e_cpu - hist[1]) if len(hist) > 1 else None, **info}
     # ---- the callers either side of the path, same inputs, one GPU: AutoRCCSD to
     #      |dE|, rms <= 1e-10 with the (T) correction, through the C ABI from host buffers.  Extra keys only;
     #      never allowed to break the line.
@@ -684,6 +673,19 @@ def gpu_arm(args, rank, world):
         except Exception as ex:     # noqa: BLE001
             next_rows = {"error": str(ex)[:300]}
     large = run_large()
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only), bounded sample.  LAST: the BLAS worker
+    #      threads of the oracle keep spinning on every host core for a while after a call, which starves the
+    #      thread that launches kernels (AutoRCCSD sweeps measured 21 ms instead of 6.4 ms right behind it)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        t_tr, t_it, e_cpu, how = run_oracle_sample(nbf, NOCC, 1, True)
+        info = cpu_info()
+        cpu = {"value": fl.rccsd_iter_ref(o, v) / t_it * 1e-12, "unit": "TFLOP/s",
+               "cores": info["blas_threads"] or info["host_cores"],
+               "kind": "port", "s_per_iteration": t_it, "s_transforms": t_tr,
+               "sample": f"oracle (numpy/OpenBLAS port of the reference's literal algorithm): 15 transforms "
+                         f"({t_tr:.1f} s) + 1 sweep ({t_it:.1f} s) at nbf={nbf} nocc={NOCC}; value = F_ref / s",
+               "energy_check": abs(e_cpu - hist[1]) if len(hist) > 1 else None, **info}
     if large:
         ds = [x for x in ((large.get(t) or {}).get(k) for t in ("strong", "c4", "c5")
                           for k in ("max_abs_dE_vs_other_rank_counts", "abs_dE_vs_other_rank_counts")) if x is not None]

@@ -92,7 +92,12 @@ int jues_b200_rmp2(jues_ctx* ctx, const double* gao, int64_t nao,
                    const double* eps, double* e_mp2);
 
 /* ---- CoupledCluster.RCCD.do_rccd (src/CoupledCluster/RCCD.jl:33-83) --------------------- */
-/* maxit Jacobi sweeps with no convergence test (reference: maxit = 40, RCCD.jl:34,55).
+/* Limit of every coupled-cluster entry point (rccd, rccsd, auto_rccsd, mrccd, df_rccd): nocc <= 158.  The
+ * kernels that combine T2 with its (i,j)-transposed partner stage one nocc x nocc block in shared memory
+ * (200 KB); a larger occupied space returns JUES_B200_EINVAL ("nocc too large ...").  The reference has no
+ * such limit; BASELINE's largest configuration has nocc = 60.
+ *
+ * maxit Jacobi sweeps with no convergence test (reference: maxit = 40, RCCD.jl:34,55).
  * guess_mode 0 = reference guess T2 = (ij|ab)/D (RCCD.jl:45,145-160); 1 = MP2 guess.
  * e_hist (nullable): [maxit+1] energies, e_hist[0] = energy of the guess, e_hist[k] after
  * sweep k.  T2_out (nullable): (nocc,nocc,nvir,nvir) final amplitudes (return_T2, RCCD.jl:36,78).
