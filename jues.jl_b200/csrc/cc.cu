@@ -305,7 +305,9 @@ struct CC {
         ctx->perm_cache = nullptr;
         pcache.clear();
         if (ctx->arena == &arena) ctx->arena = nullptr;        // members that still hold arena blocks just drop them
-        if (ev_fork) { cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
+        if (ctx->arena_main == &arena) ctx->arena_main = nullptr;
+        if (ctx->arena_side == &arena2) ctx->arena_side = nullptr;
+        if (ev_fork) { cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_fork2); cudaEventDestroy(ev_join2); }
     }
 
     double energy() { return cc_energy(ctx, V.p(), T2.p(), singles ? T1.p() : nullptr, o, v); }
@@ -366,6 +368,11 @@ struct CC {
             pcache.provide(perm_key(tauh_S, "mnaf", "mnfa"), std::move(xb[5]));
         }
 
+        // ---- small intermediates + T1 update: independent of the ring intermediates below, so this branch
+        //      (~0.7 ms of low-occupancy kernels at config 3) is issued on the second stream and runs under the
+        //      ring / ladder GEMMs; joined before the hole-hole ladder, its first consumer ------------------
+        const bool overlap = relaid && ctx->arena == &arena && ctx->arena_side == &arena2 && ctx->trace < 2 && !no_overlap();
+        SideScope side(*this, overlap);
         // ---- small intermediates: partial sums over f in the slab, one all-reduce -------------------
         TraceTimer* tr_small = new TraceTimer(ctx, "cc.part.small");
         const int64_t nFae = v * v, nFmi = o * o, nW = o * o * o * o, nR1 = o * v;
@@ -425,6 +432,7 @@ struct CC {
             contract(ctx, 0.5, Fme, "me", t, "je", 1.0, Fmi_t, "mj");
             FaeTt = FaeT_t; FmiT = Fmi_t;
         }
+        side.close();
         // ---- ring intermediates for the slab, layout [m,e,j,b] ------------------------------------
         TraceTimer* tr_ring = new TraceTimer(ctx, "cc.part.ringW");
         const size_t ns = (size_t)(o * o * v * vs);
@@ -488,6 +496,7 @@ struct CC {
         } else {
             contract(ctx, 1.0, tauv, "ijef", W4, "efab", 0.0, Lpp, "ijab");
         }
+        if (overlap) JUES_CUDA(cudaStreamWaitEvent(ctx->stream, ev_join2, 0));        // the side branch has finished
         contract(ctx, 1.0, Wpp, "mnij", tau_S, "mnab", 0.0, Lhh, "ijab");
         // ---- half residual H for the slab (its (ij)(ab) image is added by residual_finish) ----------
         contract(ctx, 1.0, T, "ijae", last_slab(FaeTt, b0, vs), "eb", 0.0, H, "ijab");
@@ -570,11 +579,14 @@ struct CC {
         use_graphs = sweeps >= 12 && fl < 1.5e12;     // < ~50 ms per sweep
     }
 
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;     // second-stream fork / join inside a sweep
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;     // second-stream fork / join inside a sweep (ladder gather)
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;   // ... (side branch: small intermediates + T1 update)
     void ensure_events() {
         if (ev_fork) return;
         JUES_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         JUES_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        JUES_CUDA(cudaEventCreateWithFlags(&ev_fork2, cudaEventDisableTiming));
+        JUES_CUDA(cudaEventCreateWithFlags(&ev_join2, cudaEventDisableTiming));
     }
 
     // Temporaries of a sweep (~300 stream-ordered allocations) come from one arena sized by the first sweep:
@@ -593,7 +605,66 @@ struct CC {
         }
         arena.reset(arena_block.p, bytes);
         ctx->arena = &arena;
+        ctx->arena_main = &arena;
+        // the side branch of the sweep (small intermediates + T1 update, issued on the second stream under the
+        // ring-intermediate GEMMs) takes its temporaries from an arena of its own
+        if (side_peak == 0 || no_overlap()) return;
+        const size_t b2 = ((side_peak + side_peak / 2 + (size_t(16) << 20)) + 255) & ~size_t(255);
+        try {
+            ArenaPause ap(ctx);
+            arena2_block.alloc(ctx, b2 / 8);
+        } catch (const Error&) {
+            cudaGetLastError();
+            return;
+        }
+        arena2.reset(arena2_block.p, b2);
+        ctx->arena_side = &arena2;
     }
+    Arena arena2;
+    DBuf arena2_block;
+    size_t side_peak = 0;          // what the side branch held at once in the measured first sweep
+    static bool no_overlap() {
+        static const bool off = getenv("JUES_B200_NO_OVERLAP") != nullptr;       // A/B switch for measurements
+        return off;
+    }
+    // The side branch runs on ctx->comm_stream from its own arena; misses go to the stream-ordered pool.
+    struct SideScope {
+        CC& cc;
+        bool on;
+        cudaStream_t saved_stream = nullptr;
+        Arena* saved_arena = nullptr;
+        size_t live0 = 0, peak0 = 0;
+        bool measuring = false;
+        SideScope(CC& c, bool enable) : cc(c), on(enable) {
+            jues_ctx* ctx = cc.ctx;
+            measuring = ctx->measure;
+            if (measuring) { live0 = ctx->temp_live; peak0 = ctx->temp_peak; ctx->temp_peak = live0; }
+            if (!on) return;
+            cc.ensure_events();
+            JUES_CUDA(cudaEventRecord(cc.ev_fork2, ctx->stream));
+            saved_stream = ctx->stream; saved_arena = ctx->arena;
+            ctx->stream = ctx->comm_stream;
+            ctx->arena = &cc.arena2;
+            ctx->no_big_cache = true;
+            JUES_CUDA(cudaStreamWaitEvent(ctx->stream, cc.ev_fork2, 0));
+        }
+        bool closed = false;
+        void close() {
+            if (closed) return;
+            closed = true;
+            jues_ctx* ctx = cc.ctx;
+            if (measuring) {
+                cc.side_peak = std::max(cc.side_peak, ctx->temp_peak - live0);
+                ctx->temp_peak = std::max(peak0, ctx->temp_peak);
+            }
+            if (!on) return;
+            cudaEventRecord(cc.ev_join2, ctx->stream);
+            ctx->stream = saved_stream; ctx->arena = saved_arena;
+            ctx->no_big_cache = false;
+            on = false;
+        }
+        ~SideScope() { close(); }
+    };
 
     void sweep() {
         static const bool no_graph = getenv("JUES_B200_NO_GRAPH") != nullptr;

@@ -146,7 +146,13 @@ struct jues_ctx {
     bool measure = false;
     size_t temp_live = 0, temp_peak = 0;
     long long big_allocs = 0;     // allocations of big_bytes or more NOT served by the arena (a sweep that makes any is not captured)
-    jues::Arena* arena = nullptr;
+    jues::Arena* arena = nullptr;          // where DBuf takes sweep temporaries from right now (nullptr: pool / block cache)
+    // every arena that may own live blocks (release looks the owner up by address): the main one and the one
+    // of the side branch of a sweep, which is issued on the second stream (the free lists assume that the blocks
+    // of one arena are used in ONE stream's order, so each concurrent branch has its own)
+    jues::Arena* arena_main = nullptr;
+    jues::Arena* arena_side = nullptr;
+    bool no_big_cache = false;             // side branch: a miss must not take a cached cudaMalloc block (not stream-ordered)
     // multi-GPU (one process per GPU): rank / world size and an NCCL communicator (opaque here)
     int rank = 0;
     int nranks = 1;
@@ -228,7 +234,7 @@ struct DBuf {
         const auto t0__ = std::chrono::steady_clock::now();
         cudaError_t e = cudaSuccess;
         cap = bytes;
-        from_big = bytes >= c->big_bytes;
+        from_big = bytes >= c->big_bytes && !c->no_big_cache;
         from_arena = false;
         counted = c->measure;
         if (counted) {
@@ -288,7 +294,10 @@ struct DBuf {
         if (p) {
             if (counted) { ctx->temp_live -= std::min(ctx->temp_live, cap); counted = false; }
             if (from_arena) {
-                if (ctx->arena && ctx->arena->has(p)) ctx->arena->give(p, cap);   // else: the arena is gone with its block
+                // back to the arena that owns the address (if it is gone, so is its block)
+                if (ctx->arena_main && ctx->arena_main->has(p)) ctx->arena_main->give(p, cap);
+                else if (ctx->arena_side && ctx->arena_side->has(p)) ctx->arena_side->give(p, cap);
+                else if (ctx->arena && ctx->arena->has(p)) ctx->arena->give(p, cap);
             } else if (from_big) {
                 ctx->big_free.emplace(cap, p);
                 ctx->big_cached_bytes += cap;
