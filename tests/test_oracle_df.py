@@ -58,3 +58,14 @@ def test_df_rccd_honours_maxit_and_returns_T2():
     e3, T3 = odf.do_df_rccd(pqP, Jpqh, C[:, :2].copy(), C[:, 2:].copy(), eps, maxit=3, return_T2=True)
     e0 = odf.do_df_rccd(pqP, Jpqh, C[:, :2].copy(), C[:, 2:].copy(), eps, maxit=0)
     assert T3.shape == (2, 2, 4, 4) and e3 != e0
+
+
+def test_mirror_setup_df_needs_the_tensors():
+    """Host side of the mirror: DF.setup_df hands back Wfn.df, and says so when it is missing (no device call)."""
+    import jues.jl_b200 as jb
+    pqP, Jpqh, C, eps = df_inputs(6, 2, 9, 3)
+    w = jb.Wfn(2, 4, eps, C[:, :2].copy(), C[:, 2:].copy(), None, Ca=C, df=(pqP, Jpqh))
+    a, b = jb.DF.setup_df(w, dfbname="cc-pvdz-ri")
+    assert a is pqP and b is Jpqh
+    with pytest.raises(jb.JuesError):
+        jb.DF.setup_df(jb.Wfn(2, 4, eps, C[:, :2].copy(), C[:, 2:].copy(), None, Ca=C))
