@@ -596,7 +596,9 @@ struct CC {
     void install_arena(size_t need) {
         if (ctx->arena || need == 0 || need > (size_t(24) << 30)) return;
         // first-fit over blocks of very different sizes fragments: half as much again as the first sweep held
-        const size_t bytes = ((need + need / 2 + (size_t(16) << 20)) + 255) & ~size_t(255);
+        // (twice while that is cheap: blocks of 64 MB and more next to small ones fragment a first-fit list)
+        const size_t slack = need < (size_t(6) << 30) ? need : need / 2;
+        const size_t bytes = ((need + slack + (size_t(16) << 20)) + 255) & ~size_t(255);
         try {
             arena_block.alloc(ctx, bytes / 8);
         } catch (const Error&) {
@@ -633,6 +635,7 @@ struct CC {
         bool on;
         cudaStream_t saved_stream = nullptr;
         Arena* saved_arena = nullptr;
+        bool saved_nbc = false;
         size_t live0 = 0, peak0 = 0;
         bool measuring = false;
         SideScope(CC& c, bool enable) : cc(c), on(enable) {
@@ -642,7 +645,7 @@ struct CC {
             if (!on) return;
             cc.ensure_events();
             JUES_CUDA(cudaEventRecord(cc.ev_fork2, ctx->stream));
-            saved_stream = ctx->stream; saved_arena = ctx->arena;
+            saved_stream = ctx->stream; saved_arena = ctx->arena; saved_nbc = ctx->no_big_cache;
             ctx->stream = ctx->comm_stream;
             ctx->arena = &cc.arena2;
             ctx->no_big_cache = true;
@@ -660,7 +663,7 @@ struct CC {
             if (!on) return;
             cudaEventRecord(cc.ev_join2, ctx->stream);
             ctx->stream = saved_stream; ctx->arena = saved_arena;
-            ctx->no_big_cache = false;
+            ctx->no_big_cache = saved_nbc;
             on = false;
         }
         ~SideScope() { close(); }
@@ -702,11 +705,18 @@ struct CC {
             bool captured = false;
             if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
                 bool threw = false;
+                // a temporary that does not fit the arena while capturing (first-fit fragmentation with blocks of
+                // 64 MB and more: seen at the 8-GPU bench shape) comes from the stream-ordered pool, i.e. becomes
+                // an allocation node owned by the graph -- never a cached cudaMalloc block, whose address the
+                // cache may hand to somebody else between replays
+                const bool nbc = ctx->no_big_cache;
+                ctx->no_big_cache = true;
                 try {
                     iterate();
                 } catch (const Error&) {
                     threw = true;
                 }
+                ctx->no_big_cache = nbc;
                 const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
                 // a sweep that took blocks from the big-block cache is not replayed: the graph would keep
                 // using addresses that the cache may hand to somebody else
