@@ -576,7 +576,7 @@ struct CC {
     void allow_graphs(int sweeps) {
         const double fl = 2.0 * (double)(o * o) * (double)(v * v) * (double)(v * v) +
                           22.0 * (double)(o * o * o) * (double)(v * v * v);
-        use_graphs = sweeps >= 12 && fl < 1.5e12;     // < ~50 ms per sweep
+        use_graphs = sweeps >= 12 && fl / (double)ctx->nranks < 1.5e12;     // < ~50 ms per sweep on this rank
     }
 
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;     // second-stream fork / join inside a sweep (ladder gather)
