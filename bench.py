@@ -468,13 +468,9 @@ def large_block(ctx, jb, dist, torch, world, rank, peak):
                             "abs_dE_vs_other_rank_counts": abs(e - ref) if ref is not None else None,
                             "peak_device_GB": c["bytes_peak"] / 1e9}
             else:
-                # first call on this context: the device blocks of this shape are allocated inside it (seconds of
-                # cudaMalloc at config 5); the transform is timed on the second call, the first one is reported too
-                jb.RCCSD.do_rccsd(w, ctx=ctx, _maxit=0)
-                tr_first = [ms for k, ms in ctx.phases() if k == "cc.transform"][0]
-                torch.cuda.synchronize()
-                if dist is not None:
-                    dist.barrier()
+                # one call: the transform is timed on a context that has never seen this shape, device block
+                # allocation included (a second call was measured SLOWER at these memory-heavy shapes -- 1.03 s
+                # against 0.74 s at nbf=300: the block cache of the first call is flushed to make room)
                 hist = []
                 ctx.set_trace(1)
                 try:
@@ -490,7 +486,7 @@ def large_block(ctx, jb, dist, torch, world, rank, peak):
                 exch_ms = sum(ms for k, ms in ph if k == "tei.exchange")
                 gen = sum(ms for k, ms in ph if k == "tei.block")
                 tr_flops = c["gemm_flops"] - sum(gf) * 1e9
-                ms_it, tr, comm_ms, gen, tr_first = allmax([ms_it, tr, comm_ms, gen, tr_first])
+                ms_it, tr, comm_ms, gen = allmax([ms_it, tr, comm_ms, gen])
                 fl_it, fl_tr = allsum([float(np.median(gf)) * 1e9, tr_flops])
                 ref = inv.get(f"rccsd_nbf{nbf}_nocc{nocc}", {}).get("e_hist")
                 d_e = float(np.abs(np.asarray(hist[:len(ref)]) - np.asarray(ref[:len(hist)])).max()) if ref else None
@@ -499,7 +495,6 @@ def large_block(ctx, jb, dist, torch, world, rank, peak):
                             "frac_of_fp64_peak_per_gpu": fl_it / (ms_it * 1e-3) * 1e-12 / world / peak,
                             "transform_s": tr * 1e-3, "transform_tflops_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world,
                             "transform_frac_of_fp64_peak_per_gpu": fl_tr / (tr * 1e-3) * 1e-12 / world / peak,
-                            "transform_s_first_call_on_context": tr_first * 1e-3,
                             "ao_generation_ms": gen,
                             "transform_tflops_per_gpu_excl_generation": fl_tr / max((tr - gen) * 1e-3, 1e-9) * 1e-12 / world,
                             "comm_ms_per_sweep": comm_ms, "transform_exchange_ms_overlapped": exch_ms,

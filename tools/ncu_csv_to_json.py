@@ -8,7 +8,11 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum"]
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "sm__inst_executed_pipe_fp64_op_dmma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed_pipe_fp64.sum", "sm__cycles_elapsed.max",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem"]
 
 
 def main(src, dst):
