@@ -35,7 +35,10 @@ def P(H):
 # ------------------------------------------------------------------------------------------
 # RCCD
 # ------------------------------------------------------------------------------------------
-def rccd_iteration(I, T, D):
+def rccd_iteration(I, T, D, relaid=False, df_wmbej=False):
+    """relaid: the second-half-of-round-2 form of the sweep (cc.cu, `relaid`): the Fmi term enters through its
+    (ij)(ab) image and the three ring products are summed in their GEMM-native layouts before they are added
+    to H.  df_wmbej: the ring intermediate of DF-RCCD.jl:248-258 (<mn|ef> where RCCD.jl:402 has <nm|ef>)."""
     V, J, oooo, vvvv = I["V"], I["J"], I["oooo"], I["vvvv"]
     Vt = 2 * V - V.transpose(1, 0, 2, 3)                      # static
     ovvo = V.transpose(0, 3, 2, 1)                             # ovvo[m,b,e,j] = V[m,j,e,b]
@@ -46,16 +49,22 @@ def rccd_iteration(I, T, D):
     X = 0.5 * es("mnef,ijef->mnij", V, T)
     Wpp = oooo + 2 * X                                          # Wmnij + X
     # ring intermediates
-    WmBeJ = ovvo + 0.5 * es("mnef,njfb->mbej", Vt, T) - 0.5 * es("mnef,jnfb->mbej", V, T)
+    WmBeJ = ovvo + 0.5 * es("mnef,njfb->mbej", V if df_wmbej else Vt, T) - 0.5 * es("mnef,jnfb->mbej", V, T)
     WmBEj = -J.transpose(0, 1, 3, 2) + 0.5 * es("nmef,jnfb->mbej", V, T)
     # ladders
     Lpp = es("ijef,abef->ijab", T, vvvv)
     Lhh = es("mnij,mnab->ijab", Wpp, T)
     # half residual
-    H = es("ijae,be->ijab", T, Fae) - es("imab,mj->ijab", T, Fmi)
-    H += es("imae,mbej->ijab", Tt, WmBeJ)
-    H += es("imae,mbej->ijab", T, WmBEj)
-    H += es("mibe,maej->ijab", T, WmBEj)
+    if relaid:
+        H = es("ijae,be->ijab", T, Fae) - es("mi,mjab->ijab", Fmi, T)      # image of - T[imab] Fmi[mj]
+        Ra = es("imae,mbej->iajb", Tt, WmBeJ) + es("imae,mbej->iajb", T, WmBEj)   # [ia|jb], as the GEMM writes it
+        Rb = es("mjae,mbei->jaib", T, WmBEj)                                       # [ja|ib]
+        H += Ra.transpose(0, 2, 1, 3) + Rb.transpose(2, 0, 1, 3)                   # ring_combine
+    else:
+        H = es("ijae,be->ijab", T, Fae) - es("imab,mj->ijab", T, Fmi)
+        H += es("imae,mbej->ijab", Tt, WmBeJ)
+        H += es("imae,mbej->ijab", T, WmBEj)
+        H += es("mibe,maej->ijab", T, WmBEj)
     R = V + Lpp + Lhh + H + P(H)
     return R / D
 
@@ -63,10 +72,12 @@ def rccd_iteration(I, T, D):
 # ------------------------------------------------------------------------------------------
 # RCCSD
 # ------------------------------------------------------------------------------------------
-def rccsd_iteration(I, t, T, Dia, D, fock=None):
+def rccsd_iteration(I, t, T, Dia, D, fock=None, relaid=False):
     """fock = (foo, fov, fvv): off-diagonal Fock blocks (zero diagonals) of a non-canonical
     reference, index order as AutoRCCSD.jl:78-80,130-131 uses them (foo[i,k], fov[k,c], fvv[c,a]).
-    None = canonical orbitals (RCCSD.jl)."""
+    None = canonical orbitals (RCCSD.jl).  relaid: the form of the sweep without output permutation passes
+    (cc.cu, `relaid`): Fmi term through its image, ring products combined in their GEMM-native layouts,
+    everything contracted with t[m,a] over m summed first, one static operand 2<am|ef> - <ma|ef>."""
     V, J, ooov, ovvv, oooo, vvvv = (I[k] for k in ("V", "J", "ooov", "ovvv", "oooo", "vvvv"))
     # ---- static combinations (built once in the library) ----
     Vt = 2 * V - V.transpose(1, 0, 2, 3)
@@ -108,19 +119,31 @@ def rccsd_iteration(I, t, T, Dia, D, fock=None):
     Lhh = es("mnij,mnab->ijab", Wpp, tau)
     Yp = es("ijef,mbef->ijmb", tau, ovvv)
     # ---- T2: half residual ----
-    H = es("ijae,be->ijab", T, Fae_t) - es("imab,mj->ijab", T, Fmi_t)
-    H -= es("ijmb,ma->ijab", Yp, t)
-    H += es("imae,mbej->ijab", Tt, WmBeJ)
-    H += es("imae,mbej->ijab", T, WmBEj)
-    H += es("mibe,maej->ijab", T, WmBEj)
-    # rank-1 ring corrections: - t[ie] t[ma] ovvo[mbej] - t[ie] t[mb] vovo[amej]
-    Z1 = es("ma,mbej->abej", t, ovvo)
-    H -= es("ie,abej->ijab", t, Z1)
-    Z2 = es("mb,maje->baje", t, J)                 # vovo[a,m,e,j] = (ae|mj) = J[m,a,j,e]
-    H -= es("ie,baje->ijab", t, Z2)
-    # t . (vvvo) and t . (ovoo):  vvvo[e,a,b,j] = ovvv[j,a,b,e];  ovoo[m,b,i,j] = ooov[m,j,i,b]
-    H += es("ie,jabe->ijab", t, ovvv)
-    H -= es("ma,mjib->ijab", t, ooov)
+    if relaid:
+        H = es("ijae,be->ijab", T, Fae_t) - es("mi,mjab->ijab", Fmi_t, T)    # image of - T[imab] Fmi[mj]
+        Ra = es("imae,mbej->iajb", Tt, WmBeJ) + es("imae,mbej->iajb", T, WmBEj)
+        Rb = es("mjae,mbei->jaib", T, WmBEj)
+        H += Ra.transpose(0, 2, 1, 3) + Rb.transpose(2, 0, 1, 3)                # ring_combine
+        # everything contracted with t[m,a] over m: <mj|ib> + tau[ijef] <ef|mb> + t[ie] <mj|eb>
+        Ysum = ooov.transpose(2, 1, 0, 3) + Yp + es("ie,mjeb->ijmb", t, V)
+        H -= es("ijmb,ma->ijab", Ysum, t)
+        Z2 = es("ie,maje->imaj", t, J)
+        H -= es("imaj,mb->ijab", Z2, t)
+        H += es("ie,jabe->ijab", t, ovvv)
+    else:
+        H = es("ijae,be->ijab", T, Fae_t) - es("imab,mj->ijab", T, Fmi_t)
+        H -= es("ijmb,ma->ijab", Yp, t)
+        H += es("imae,mbej->ijab", Tt, WmBeJ)
+        H += es("imae,mbej->ijab", T, WmBEj)
+        H += es("mibe,maej->ijab", T, WmBEj)
+        # rank-1 ring corrections: - t[ie] t[ma] ovvo[mbej] - t[ie] t[mb] vovo[amej]
+        Z1 = es("ma,mbej->abej", t, ovvo)
+        H -= es("ie,abej->ijab", t, Z1)
+        Z2 = es("mb,maje->baje", t, J)                 # vovo[a,m,e,j] = (ae|mj) = J[m,a,j,e]
+        H -= es("ie,baje->ijab", t, Z2)
+        # t . (vvvo) and t . (ovoo):  vvvo[e,a,b,j] = ovvv[j,a,b,e];  ovoo[m,b,i,j] = ooov[m,j,i,b]
+        H += es("ie,jabe->ijab", t, ovvv)
+        H -= es("ma,mjib->ijab", t, ooov)
     R2 = V + Lpp + Lhh + H + P(H)
     return R1 / Dia, R2 / D
 

@@ -4,6 +4,7 @@ expressions are the conventional ones."""
 import numpy as np
 import pytest
 
+import factorized_model as fm
 from oracle import jues_oracle as orc
 from oracle import jues_oracle_df as odf
 
@@ -37,6 +38,7 @@ def test_df_equals_conventional_for_an_exact_factorisation(nbf, nocc, naux):
     w = orc.Wfn(nocc, nvir, eps, C[:, :nocc].copy(), C[:, nocc:].copy(), gao)
     assert abs(odf.do_df_rmp2(pqP, Jpqh, C, nocc, nvir, eps) - orc.do_rmp2(w)) < 1e-13
     ints = orc.make_rccd_integrals(gao, w.Cao, w.Cav)
+    I6 = fm.unique_integrals(gao, w.Cao, w.Cav)
     oovv, ovov, ovvo, oooo, vvvv = ints
     D = orc.form_Dijab(nocc, nvir, eps)
     T = oovv / D
@@ -50,7 +52,10 @@ def test_df_equals_conventional_for_an_exact_factorisation(nbf, nocc, naux):
         Fae, Fmi, Wabef, Wmnij, WmBeJ, WmBEj = orc.rccd_intermediates(T, *ints)
         WmBeJ_df = ovvo + es("mnef,njfb->mbej", oovv, T - T.transpose(1, 0, 2, 3)) / 2
         assert np.abs(WmBeJ_df - WmBeJ).max() > 1e-6         # the two references do differ here
-        T = orc.rccd_residual(T, Fae, Fmi, WmBeJ_df, WmBEj, Wabef, Wmnij, oovv) / D
+        T_next = orc.rccd_residual(T, Fae, Fmi, WmBeJ_df, WmBEj, Wabef, Wmnij, oovv) / D
+        # ... and the numpy statement of what the device runs for it (re-laid sweep, DF ring intermediate)
+        assert np.abs(fm.rccd_iteration(I6, T, D, relaid=True, df_wmbej=True) - T_next).max() < 1e-13
+        T = T_next
 
 
 def test_df_rccd_honours_maxit_and_returns_T2():

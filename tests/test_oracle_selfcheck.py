@@ -44,6 +44,30 @@ def test_factorized_rccsd_equals_literal(N, o, seed):
         t1, T = a, b
 
 
+@pytest.mark.parametrize("N,o,seed", [(8, 3, 1), (12, 4, 9)])
+def test_relaid_sweep_equals_literal(N, o, seed):
+    """The form of the sweep without output permutation passes (cc.cu `relaid`: Fmi term through its (ij)(ab)
+    image, ring products combined in their GEMM-native layouts, terms contracted with t[m,a] summed first) is the
+    same iteration.  The image trick relies on T2[i,j,a,b] = T2[j,i,b,a], which every iterate satisfies."""
+    g, Cao, Cav, eps, w = inputs(N, o, seed)
+    v = N - o
+    I6 = fm.unique_integrals(g, Cao, Cav)
+    I = orc.make_rccsd_integrals(g, Cao, Cav)
+    ints = orc.make_rccd_integrals(g, Cao, Cav)
+    D, Dia = orc.form_Dijab(o, v, eps), orc.form_Dia(o, v, eps)
+    t1, T = np.zeros((o, v)), I["oovv"] / D
+    for _ in range(5):
+        a, b = orc.rccsd_iteration(I, t1, T, Dia, D)
+        c, d = fm.rccsd_iteration(I6, t1, T, Dia, D, relaid=True)
+        assert np.abs(a - c).max() < 1e-14 and np.abs(b - d).max() < 1e-14
+        t1, T = a, b
+    T = orc.rccd_guess(ints[1], D)
+    for _ in range(4):
+        Tr = orc.rccd_iteration(T, ints, D)
+        assert np.abs(Tr - fm.rccd_iteration(I6, T, D, relaid=True)).max() < 1e-14
+        T = Tr
+
+
 def test_integral_class_identities():
     """The 15 classes of make_rccsd_integrals (RCCSD.jl:117-142) reduce to six."""
     g, Cao, Cav, eps, w = inputs(9, 3, 5)
