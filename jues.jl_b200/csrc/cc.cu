@@ -371,7 +371,10 @@ struct CC {
         // ---- small intermediates + T1 update: independent of the ring intermediates below, so this branch
         //      (~0.7 ms of low-occupancy kernels at config 3) is issued on the second stream and runs under the
         //      ring / ladder GEMMs; joined before the hole-hole ladder, its first consumer ------------------
-        const bool overlap = relaid && ctx->arena == &arena && ctx->arena_side == &arena2 && ctx->trace < 2 && !no_overlap();
+        // (only for short sweeps: at nbf=300 on 2 GPUs the branch's own large GEMMs competing with the ring
+        // products cost 2 %, 0.892 against 0.875 s)
+        const bool overlap = relaid && short_sweeps() && ctx->arena == &arena && ctx->arena_side == &arena2 &&
+                             ctx->trace < 2 && !no_overlap();
         SideScope side(*this, overlap);
         // ---- small intermediates: partial sums over f in the slab, one all-reduce -------------------
         TraceTimer* tr_small = new TraceTimer(ctx, "cc.part.small");
@@ -573,11 +576,13 @@ struct CC {
     // Capturing + instantiating the two graphs costs ~80 ms of host time (measured, nbf = 120), so the
     // driver turns replay on only for long fixed-length runs of launch-bound sweeps (see allow_graphs).
     bool use_graphs = false;
-    void allow_graphs(int sweeps) {
+    // sweeps of less than ~50 ms on this rank: launch- and latency-bound kernels are a visible share
+    bool short_sweeps() const {
         const double fl = 2.0 * (double)(o * o) * (double)(v * v) * (double)(v * v) +
                           22.0 * (double)(o * o * o) * (double)(v * v * v);
-        use_graphs = sweeps >= 12 && fl / (double)ctx->nranks < 1.5e12;     // < ~50 ms per sweep on this rank
+        return fl / (double)ctx->nranks < 1.5e12;
     }
+    void allow_graphs(int sweeps) { use_graphs = sweeps >= 12 && short_sweeps(); }
 
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;     // second-stream fork / join inside a sweep (ladder gather)
     cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;   // ... (side branch: small intermediates + T1 update)
