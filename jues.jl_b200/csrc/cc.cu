@@ -310,8 +310,8 @@ struct CC {
         if (ev_fork) { cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_fork2); cudaEventDestroy(ev_join2); }
     }
 
-    double energy() { return cc_energy(ctx, V.p(), T2.p(), singles ? T1.p() : nullptr, o, v); }
-    void energy_async(double* dev_out) { cc_energy_async(ctx, V.p(), T2.p(), singles ? T1.p() : nullptr, o, v, dev_out); }
+    double energy() { return cc_energy(ctx, Vt.p(), T2.p(), singles ? T1.p() : nullptr, o, v); }
+    void energy_async(double* dev_out) { cc_energy_async(ctx, Vt.p(), T2.p(), singles ? T1.p() : nullptr, o, v, dev_out); }
 
     void guess(int guess_mode) {
         T2.alloc(ctx, o, o, v, v); T2n.alloc(ctx, o, o, v, v);

@@ -375,71 +375,45 @@ __device__ __forceinline__ double block_reduce(double v) {
     return r;  // valid in thread 0
 }
 
-// E = sum V[ijab] (2 X[ijab] - X[jiab]), X = T + t(x)t.  One block per group of (a,b) slabs; the o x o block
-// of T goes through shared memory (its transposed partner is in the same block), V and T move as 16-byte
-// vectors along i (o is even).
-template <bool WARP>
-__global__ void cc_energy_kernel(const double* __restrict__ V, const double* __restrict__ T,
-                                 const double* __restrict__ t1, int o, int v, double* __restrict__ partial) {
-    extern __shared__ double sh_all[];  // per pair o x (o+1): sh[j*(o+1)+i] = T[i,j,a,b]
-    const PairLoop L(WARP);
-    double* sh = sh_all + (size_t)L.wid * o * (o + 1);
-    const long long oo = (long long)o * o;
+// E = sum V[ijab] (2 X[ijab] - X[jiab]) = sum Vt[ijab] X[ijab] with the static Vt = 2V - V(ji) (relabel i <-> j in
+// the second term) and X = T + t(x)t: a plain dot product of two contiguous arrays -- no transposed partner, no
+// shared memory, no barrier.  16-byte accesses along i (o is even), four independent pairs of loads per thread in
+// flight; fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) cc_energy_kernel(const double* __restrict__ Vt, const double* __restrict__ T,
+                                                        const double* __restrict__ t1, int o, int v,
+                                                        double* __restrict__ partial) {
+    const long long n2 = (long long)o * o * v * v / 2;          // double2 elements
     const int half = o >> 1;
-    double acc = 0.0;
-    for (long long ab = (long long)blockIdx.x * L.nw + L.wid; ab < (long long)v * v; ab += (long long)gridDim.x * L.nw) {
-        const int a = (int)(ab % v), b = (int)(ab / v);
-        const long long base = ab * oo;
-        // four independent 16-byte loads in flight per thread in both passes (a pure-read kernel: with one
-        // load per loop trip the FMA chain behind it serialises the memory requests)
-        const int n2 = half * o;
-        for (int e0 = L.tid; e0 < n2; e0 += 4 * L.nt) {
-            double2 x[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * L.nt;
-                if (e < n2) x[u] = *reinterpret_cast<const double2*>(T + base + 2 * (e % half) + (long long)o * (e / half));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * L.nt;
-                if (e < n2) {
-                    const int i = 2 * (e % half), j = e / half;
-                    sh[j * (o + 1) + i] = x[u].x;
-                    sh[j * (o + 1) + i + 1] = x[u].y;
-                }
-            }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double2* __restrict__ V2 = reinterpret_cast<const double2*>(Vt);
+    const double2* __restrict__ T2 = reinterpret_cast<const double2*>(T);
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    auto term = [&](long long L, const double2 vv, const double2 x) {
+        double x0 = x.x, x1 = x.y;
+        if (t1) {
+            // L -> (i pair, j, a, b)
+            long long r = L;
+            const int ip = (int)(r % half); r /= half;
+            const int j = (int)(r % o); r /= o;
+            const int a = (int)(r % v);
+            const int b = (int)(r / v);
+            const double2 ta = *reinterpret_cast<const double2*>(t1 + 2 * ip + (long long)o * a);
+            const double tb = t1[j + (long long)o * b];
+            x0 += ta.x * tb; x1 += ta.y * tb;
         }
-        pair_sync<WARP>();
-        for (int e0 = L.tid; e0 < n2; e0 += 4 * L.nt) {
-            double2 vq[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * L.nt;
-                if (e < n2) vq[u] = *reinterpret_cast<const double2*>(V + base + 2 * (e % half) + (long long)o * (e / half));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = e0 + u * L.nt;
-                if (e >= n2) continue;
-                const int i = 2 * (e % half), j = e / half;
-                const double2 vv = vq[u];
-                double x0 = sh[j * (o + 1) + i], x1 = sh[j * (o + 1) + i + 1];
-                double xt0 = sh[i * (o + 1) + j], xt1 = sh[(i + 1) * (o + 1) + j];
-                if (t1) {
-                    const double2 tia = *reinterpret_cast<const double2*>(t1 + i + (long long)o * a);
-                    const double2 tib = *reinterpret_cast<const double2*>(t1 + i + (long long)o * b);
-                    const double tjb = t1[j + (long long)o * b], tja = t1[j + (long long)o * a];
-                    x0 += tia.x * tjb; x1 += tia.y * tjb;
-                    xt0 += tja * tib.x; xt1 += tja * tib.y;
-                }
-                acc += vv.x * (2.0 * x0 - xt0);
-                acc += vv.y * (2.0 * x1 - xt1);
-            }
-        }
-        pair_sync<WARP>();
+        return vv.x * x0 + vv.y * x1;
+    };
+    long long L = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; L + 3 * stride < n2; L += 4 * stride) {
+        const double2 v0 = V2[L], v1 = V2[L + stride], v2 = V2[L + 2 * stride], v3 = V2[L + 3 * stride];
+        const double2 x0 = T2[L], x1 = T2[L + stride], x2 = T2[L + 2 * stride], x3 = T2[L + 3 * stride];
+        acc0 += term(L, v0, x0);
+        acc1 += term(L + stride, v1, x1);
+        acc2 += term(L + 2 * stride, v2, x2);
+        acc3 += term(L + 3 * stride, v3, x3);
     }
-    const double r = block_reduce<256>(acc);
+    for (; L < n2; L += stride) acc0 += term(L, V2[L], T2[L]);
+    const double r = block_reduce<256>((acc0 + acc1) + (acc2 + acc3));
     if (threadIdx.x == 0) partial[blockIdx.x] = r;
 }
 
@@ -881,29 +855,26 @@ static double finish_reduction(jues_ctx* ctx, int nblocks) {
     return ctx->red_host[0];
 }
 
-static int cc_energy_launch(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v) {
-    PairLaunch g = pair_launch(ctx, o, (long long)v * v, "cc_energy");
+static int cc_energy_launch(jues_ctx* ctx, const double* Vt, const double* T, const double* t1, int64_t o, int64_t v) {
+    JUES_REQUIRE((o & 1) == 0, "cc_energy: padded nocc must be even");
     AuxTimer tm(ctx, "cc_energy", 8.0 * (double)(o * o * v * v) * 2.0);
-    g.blocks = (unsigned)std::min<long long>(g.blocks, (long long)ctx->red_cap - 2);
-    if (g.warp) {
-        cc_energy_kernel<true><<<g.blocks, 256, g.smem, ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
-    } else {
-        raise_smem(ctx, cc_energy_kernel<false>);
-        cc_energy_kernel<false><<<g.blocks, 256, g.smem, ctx->stream>>>(V, T, t1, (int)o, (int)v, ctx->red_dev);
-    }
+    const size_t n2 = (size_t)(o * o * v * v) / 2;
+    int blocks = ew_grid(ctx, (n2 + 3) / 4, 256);                        // four pairs of loads per thread
+    blocks = (int)std::min<long long>(blocks, (long long)ctx->red_cap - 2);
+    cc_energy_kernel<<<blocks, 256, 0, ctx->stream>>>(Vt, T, t1, (int)o, (int)v, ctx->red_dev);
     AUX_LAUNCHED(ctx);
-    return (int)g.blocks;
+    return blocks;
 }
 
-void cc_energy_async(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v,
+void cc_energy_async(jues_ctx* ctx, const double* Vt, const double* T, const double* t1, int64_t o, int64_t v,
                      double* dev_out) {
-    const int blocks = cc_energy_launch(ctx, V, T, t1, o, v);
+    const int blocks = cc_energy_launch(ctx, Vt, T, t1, o, v);
     final_reduce_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red_dev, blocks, dev_out);
     AUX_LAUNCHED(ctx);
 }
 
-double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v) {
-    const int blocks = cc_energy_launch(ctx, V, T, t1, o, v);
+double cc_energy(jues_ctx* ctx, const double* Vt, const double* T, const double* t1, int64_t o, int64_t v) {
+    const int blocks = cc_energy_launch(ctx, Vt, T, t1, o, v);
     return finish_reduction(ctx, blocks);
 }
 

@@ -100,10 +100,11 @@ void divide_Dia(jues_ctx* ctx, const double* R1, double* tnew, const double* eo,
                 int64_t o, int64_t v);
 
 // deterministic reductions (fixed-shape two-pass tree); result returned on the host
-// E = sum_{ijab} V[ijab] * (2*X[ijab] - X[jiab]),  X = T + t(x)t (t nullable)
-double cc_energy(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v);
+// E = sum_{ijab} V[ijab] * (2*X[ijab] - X[jiab]) = sum_{ijab} Vt[ijab] * X[ijab],  X = T + t(x)t (t nullable),
+// Vt = 2V - V(ji) (the static combination the sweep already holds): a plain dot product
+double cc_energy(jues_ctx* ctx, const double* Vt, const double* T, const double* t1, int64_t o, int64_t v);
 // same reduction, result left in dev_out[0] (no host synchronisation)
-void cc_energy_async(jues_ctx* ctx, const double* V, const double* T, const double* t1, int64_t o, int64_t v,
+void cc_energy_async(jues_ctx* ctx, const double* Vt, const double* T, const double* t1, int64_t o, int64_t v,
                      double* dev_out);
 // E = sum_{ijab} v[ijab] (2 v[ijab] - v[ijba]) / (eo[i]+eo[j]-ev[a]-ev[b])
 // v is the last-index slab (o,o,vv,vs) of <ij|ab>, b in [b0, b0+vs); v_ijba is taken as v_jiab
