@@ -71,6 +71,24 @@ def rccsd_iter_alg(o, v):
     return 2 * o**2 * v**4 + 22 * o**3 * v**3 + 4 * o**4 * v**2 + 24 * o**2 * v**3 + 24 * o**3 * v**2
 
 
+def rccsd_iter_exec(o, v):
+    """FP64 operations the GEMM launches of ONE factorised RCCSD sweep of the library execute on one rank
+    (csrc/cc.cu with the packed ladder; the library counts them per launch, this is the same sum in closed
+    form, within 0.1 % at nbf=120 and 0.5 % over 8 ranks): packed pp-ladder 4 o^2 np nq with np = v(v+1)/2
+    summed pairs and nq = v(v/2+1) output pairs, seven (ov)^3-sized products (six rings + tau.<ef|mb>), and the
+    lower-order terms.  This is the unit of work both bench arms divide by their seconds, so that the ratio of
+    their `value`s is the ratio of their times."""
+    np_, nq = v * (v + 1) // 2, v * (v // 2 + 1)
+    return (4 * o**2 * np_ * nq + 14 * o**3 * v**3 + 12 * o**2 * v**3 + 18 * o**3 * v**2 + 4 * o**4 * v**2
+            + 2 * o * v**3 + 2 * o**2 * v**2)
+
+
+def cc_transform_exec(N):
+    """FP64 operations of the one-pass transform that yields every integral class of a CC run (8 N^5 over all
+    ranks; exact on one rank, +1 % padding over 8)."""
+    return 8 * N**5
+
+
 def rccd_transforms_ref(N, o, v):
     """The 5 literal transforms of make_rccd_integrals (RCCD.jl:85-97)."""
     return (tei_flops_ref(N, o, v, o, v) + tei_flops_ref(N, v, v, v, v) + tei_flops_ref(N, o, v, v, o)
