@@ -3,6 +3,7 @@
 // epilogue, synthetic ERI generator).  All reductions are deterministic (fixed two-pass tree).
 #include "tensor_ops.h"
 #include "api_util.h"
+#include "synth_element.h"
 #include <algorithm>
 
 namespace jues {
@@ -581,19 +582,13 @@ __global__ void synth_eri_kernel(double* __restrict__ g, long long n, long long 
         const unsigned long long sig = (unsigned long long)(r / lam_count) + sig_lo;
         double* __restrict__ dst = g + row * np;
         const bool live = nu < (unsigned long long)n && lam < (unsigned long long)n && sig < (unsigned long long)n;
-        const unsigned long long hi2 = lam > sig ? lam : sig, lo2 = lam > sig ? sig : lam;
-        const unsigned long long Q = hi2 * (hi2 + 1) / 2 + lo2;
-        for (unsigned long long mu = lane; mu < (unsigned long long)np; mu += 32) {
+        // n < 65536 (checked by the launcher): pair indices in 32 bits, one wide multiply per element
+        // (synth_element.h, the same function a host build compares bit for bit with the numpy generator)
+        const uint32_t Q = synth_pair32((uint32_t)lam, (uint32_t)sig);
+        const uint32_t nu32 = (uint32_t)nu;
+        for (uint32_t mu = lane; mu < (uint32_t)np; mu += 32) {
             double val = 0.0;
-            if (live && mu < (unsigned long long)n) {
-                const unsigned long long hi = mu > nu ? mu : nu, lo = mu > nu ? nu : mu;
-                const unsigned long long P = hi * (hi + 1) / 2 + lo;
-                const unsigned long long h2 = P > Q ? P : Q, l2 = P > Q ? Q : P;
-                const unsigned long long K = h2 * (h2 + 1) / 2 + l2;
-                const unsigned long long h = splitmix64(seed ^ K);
-                const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
-                val = scale * (2.0 * u - 1.0);
-            }
+            if (live && mu < (uint32_t)n) val = synth_value(synth_pair32(mu, nu32), Q, seed, scale);
             dst[mu] = val;
         }
     }
@@ -975,6 +970,7 @@ void synth_eri_block(jues_ctx* ctx, double* g, int64_t n_logical, int64_t n_padd
                      bool phys) {
     const size_t total = (size_t)n_padded * n_padded * lam_cnt * sig_cnt;
     if (!total) return;
+    JUES_REQUIRE(n_padded < 65536, "synthetic ERIs: more than 65535 basis functions");
     long long blocks = (long long)((total / (size_t)n_padded + 7) / 8);    // 8 rows (warps) per block
     const long long capb = (long long)ctx->sm_count * 32;
     if (blocks > capb) blocks = capb;
